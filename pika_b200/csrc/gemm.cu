@@ -1,0 +1,440 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: C = epilogue(alpha * sum_p A_p * B_p^T).
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      MMA issuer     (one thread: tcgen05.mma kind::f16, fp32 accumulators in TMEM,
+//                               tcgen05.commit frees smem stages / publishes the accumulator)
+//   warps 2..5  epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> swizzled smem
+//                               -> TMA store; double-buffered TMEM accumulators overlap it with
+//                               the next tile's main loop)
+// Tile 128 x BN x 64 (BN = 64 | 128 | 256).  Operands may be K-major or MN-major (wgrad / dgrad /
+// P.V use the MN-major form so no transposes are ever materialised).  Up to 9 (A,B) pairs
+// accumulate into one tile (TDNN taps, split-bf16 fp32-class mode), plus a batched reduction
+// loop (kz) for per-utterance wgrad.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/pika_b200.h"
+#include "common.cuh"
+
+namespace pk {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int C_STAGE_BYTES = BM * 128;      // 128 rows x 128 B
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+    CUtensorMap a[PK_GEMM_MAX_PAIRS];
+    CUtensorMap b[PK_GEMM_MAX_PAIRS];
+    CUtensorMap c;
+    int a_off[PK_GEMM_MAX_PAIRS];
+    int b_off[PK_GEMM_MAX_PAIRS];
+    int n_pairs, kz_count, num_k_blocks;
+    int M, N, tiles_m, tiles_n, zb0, zb1;
+    int a_sel2, a_sel3, b_sel2, b_sel3;
+    int c_is_f32, c_accumulate;
+    float alpha;
+    const float* bias;
+    int act;
+    uint32_t drop_thresh;
+    float drop_scale;
+    uint32_t drop_seed;
+    int aux_mode, aux_is_f32;
+    const void* aux;
+    long long aux_sm, aux_s0, aux_s1;
+    float aux_scale;
+};
+
+template <int BN> struct GemmCfg {
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int C_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BIAS_OFF = C_OFF + 2 * C_STAGE_BYTES;
+    static constexpr int BAR_OFF = BIAS_OFF + BN * 4;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + barriers + alignment slack
+    static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator (>= 32, pow2)
+};
+
+PK_DEVICE int pick_sel(int sel, int zb0, int zb1, int kz) {
+    return sel == PK_SEL_ZB0 ? zb0 : (sel == PK_SEL_ZB1 ? zb1 : (sel == PK_SEL_KZ ? kz : 0));
+}
+
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* bias_smem = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < p.n_pairs; ++i) {
+            tma_prefetch_desc(&p.a[i]);
+            tma_prefetch_desc(&p.b[i]);
+        }
+        tma_prefetch_desc(&p.c);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_z = p.tiles_m * p.tiles_n;
+    const int num_tiles = tiles_per_z * p.zb0 * p.zb1;
+    const int k_iters = p.n_pairs * p.kz_count * p.num_k_blocks;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int z = tile / tiles_per_z;
+                const int r = tile - z * tiles_per_z;
+                const int mb = r / p.tiles_n, nb = r - mb * p.tiles_n;
+                const int zb1 = z / p.zb0, zb0 = z - zb1 * p.zb0;
+                const int m0 = mb * BM, n0 = nb * BN;
+                for (int pr = 0; pr < p.n_pairs; ++pr) {
+                    for (int kz = 0; kz < p.kz_count; ++kz) {
+                        const int a2 = pick_sel(p.a_sel2, zb0, zb1, kz), a3 = pick_sel(p.a_sel3, zb0, zb1, kz);
+                        const int b2 = pick_sel(p.b_sel2, zb0, zb1, kz), b3 = pick_sel(p.b_sel3, zb0, zb1, kz);
+                        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                            uint8_t* sb = sa + A_STAGE_BYTES;
+                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                            if (A_MN) {
+#pragma unroll
+                                for (int i = 0; i < BM / 64; ++i)
+                                    tma_load_4d(sa + i * (64 * BK * 2), &p.a[pr], &full_bar[stage], m0 + i * 64,
+                                                kb * BK + p.a_off[pr], a2, a3);
+                            } else {
+                                tma_load_4d(sa, &p.a[pr], &full_bar[stage], kb * BK, m0 + p.a_off[pr], a2, a3);
+                            }
+                            if (B_MN) {
+#pragma unroll
+                                for (int i = 0; i < BN / 64; ++i)
+                                    tma_load_4d(sb + i * (64 * BK * 2), &p.b[pr], &full_bar[stage], n0 + i * 64,
+                                                kb * BK + p.b_off[pr], b2, b3);
+                            } else {
+                                tma_load_4d(sb, &p.b[pr], &full_bar[stage], kb * BK, n0 + p.b_off[pr], b2, b3);
+                            }
+                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int k = 0; k < k_iters; ++k) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < BK / 16; ++k4) {
+                        // K-major: 16 elements = 32 B inside the 128 B swizzle row; atoms of 8 rows (1024 B).
+                        // MN-major: 16 k-rows = two 8-row atoms (2048 B); 64-wide MN chunks 8192 B apart.
+                        const uint64_t ad = A_MN ? make_smem_desc_sw128(sa + k4 * 2048, 64 * BK * 2, 1024)
+                                                 : make_smem_desc_sw128(sa + k4 * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? make_smem_desc_sw128(sb + k4 * 2048, 64 * BK * 2, 1024)
+                                                 : make_smem_desc_sw128(sb + k4 * 32, 16, 1024);
+                        umma_bf16(d_tmem, ad, bd, idesc, (k > 0 || k4 > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===================================================== epilogue (warps 2..5)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // tile row owned by this thread
+        const int et = threadIdx.x - 64;        // 0..127
+        const bool store_thread = (et == 0);
+        const int CH = p.c_is_f32 ? 32 : 64;    // columns per 128-byte staging row
+        uint8_t* cst = smem + Cfg::C_OFF;
+        int it = 0;
+        uint32_t chunk_ctr = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int z = tile / tiles_per_z;
+            const int r = tile - z * tiles_per_z;
+            const int mb = r / p.tiles_n, nb = r - mb * p.tiles_n;
+            const int zb1 = z / p.zb0, zb0 = z - zb1 * p.zb0;
+            const int m0 = mb * BM, n0 = nb * BN;
+            const int acc = it & 1;
+            const int m = m0 + row;
+            if (p.bias != nullptr) {
+                named_bar_sync(2, 128);         // previous tile's readers are done with bias_smem
+                for (int j = et; j < BN; j += 128) bias_smem[j] = (n0 + j < p.N) ? p.bias[n0 + j] : 0.f;
+                named_bar_sync(2, 128);
+            }
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            const int n_chunks = BN / CH;
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const int nc0 = n0 + ch * CH;
+                if (nc0 >= p.N) break;           // uniform across the 4 epilogue warps
+                uint32_t v[64];
+                {
+                    uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+                    tmem_ld_32x32(t_addr + ch * CH, v0);
+                    if (CH == 64) {
+                        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+                        tmem_ld_32x32(t_addr + ch * CH + 32, v1);
+                    }
+                    tmem_ld_wait();
+                }
+                // ---- fused epilogue on this thread's row segment
+                const bool row_ok = m < p.M;
+                const unsigned char* auxp = nullptr;
+                if (p.aux_mode != PK_AUX_NONE && row_ok) {
+                    long long off = (long long)m * p.aux_sm + (long long)zb0 * p.aux_s0 + (long long)zb1 * p.aux_s1 + nc0;
+                    auxp = reinterpret_cast<const unsigned char*>(p.aux) + off * (p.aux_is_f32 ? 4 : 2);
+                }
+                const uint64_t lin_row = ((uint64_t)(zb1 * p.zb0 + zb0) * (uint64_t)p.M + (uint64_t)m) * (uint64_t)p.N;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    if (j < CH) {
+                        float x = __uint_as_float(v[j]) * p.alpha;
+                        if (p.bias != nullptr) x += bias_smem[ch * CH + j];
+                        if (p.act == PK_ACT_RELU) x = fmaxf(x, 0.f);
+                        if (p.drop_thresh != 0u) {
+                            x = drop_keep(lin_row + (uint64_t)(nc0 + j), p.drop_seed, p.drop_thresh) ? x * p.drop_scale : 0.f;
+                        }
+                        if (auxp != nullptr && nc0 + j < p.N) {
+                            const float a = p.aux_is_f32 ? reinterpret_cast<const float*>(auxp)[j]
+                                                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(auxp)[j]);
+                            if (p.aux_mode == PK_AUX_ADD) x += a;
+                            else x = (a != 0.f) ? x * p.aux_scale : 0.f;
+                        }
+                        v[j] = __float_as_uint(x);
+                    }
+                }
+                // ---- stage into 128B-swizzled smem, then one thread issues the TMA store
+                uint8_t* sbuf = cst + (chunk_ctr & 1) * C_STAGE_BYTES;
+                if (store_thread) tma_store_wait_read<1>();     // the buffer used two chunks ago is free
+                named_bar_sync(1, 128);
+                uint8_t* srow = sbuf + row * 128;
+                if (p.c_is_f32) {
+#pragma unroll
+                    for (int c16 = 0; c16 < 8; ++c16) {
+                        uint4 w = make_uint4(v[c16 * 4 + 0], v[c16 * 4 + 1], v[c16 * 4 + 2], v[c16 * 4 + 3]);
+                        *reinterpret_cast<uint4*>(srow + ((c16 ^ (row & 7)) << 4)) = w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c16 = 0; c16 < 8; ++c16) {
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(v[c16 * 8 + 0]), __uint_as_float(v[c16 * 8 + 1]));
+                        w.y = pack_bf16x2(__uint_as_float(v[c16 * 8 + 2]), __uint_as_float(v[c16 * 8 + 3]));
+                        w.z = pack_bf16x2(__uint_as_float(v[c16 * 8 + 4]), __uint_as_float(v[c16 * 8 + 5]));
+                        w.w = pack_bf16x2(__uint_as_float(v[c16 * 8 + 6]), __uint_as_float(v[c16 * 8 + 7]));
+                        *reinterpret_cast<uint4*>(srow + ((c16 ^ (row & 7)) << 4)) = w;
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (store_thread) {
+                    if (p.c_accumulate) tma_reduce_add_4d(&p.c, sbuf, nc0, m0, zb0, zb1);
+                    else tma_store_4d(&p.c, sbuf, nc0, m0, zb0, zb1);
+                    tma_store_commit();
+                }
+                ++chunk_ctr;
+            }
+            // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (store_thread) tma_store_wait<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+// Build a rank-4 tiled tensor map with 128B swizzle.  box0 * elem_size must be 128 bytes.
+static int make_map(CUtensorMap* out, const pk_view4& v, int is_f32, int box0, int box1, const char* what) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return -3; }
+    const int es = is_f32 ? 4 : 2;
+    cuuint64_t dims[4];
+    cuuint64_t strides[3];
+    cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)box1, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) {
+        if (v.dim[i] <= 0) { set_last_error("gemm %s: dim[%d]=%lld must be > 0", what, i, (long long)v.dim[i]); return -1; }
+        dims[i] = (cuuint64_t)v.dim[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+        long long sb = (long long)v.stride[i] * es;
+        if (v.dim[i + 1] == 1 && sb <= 0) sb = 16;       // unused dimension: any legal stride
+        if (sb <= 0 || (sb % 16) != 0) {
+            set_last_error("gemm %s: stride[%d]=%lld elements is not a positive multiple of 16 bytes", what, i,
+                           (long long)v.stride[i]);
+            return -1;
+        }
+        strides[i] = (cuuint64_t)sb;
+    }
+    if ((reinterpret_cast<uintptr_t>(v.ptr) & 15) != 0) { set_last_error("gemm %s: base pointer not 16B aligned", what); return -1; }
+    if ((cuuint64_t)box[1] > 256) { set_last_error("gemm %s: box too large", what); return -1; }
+    CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                     const_cast<void*>(v.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("gemm %s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r); return -3; }
+    return 0;
+}
+
+void count_launch();
+
+template <bool A_MN, bool B_MN, int BN>
+static int launch_gemm(const GemmParams& gp, int grid, cudaStream_t stream) {
+    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN>;
+    static bool configured = false;
+    if (!configured) {
+        PK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+        configured = true;
+    }
+    kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(gp);
+    PK_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+template <int BN>
+static int dispatch_major(const GemmParams& gp, int a_mn, int b_mn, int grid, cudaStream_t stream) {
+    if (!a_mn && !b_mn) return launch_gemm<false, false, BN>(gp, grid, stream);
+    if (!a_mn && b_mn) return launch_gemm<false, true, BN>(gp, grid, stream);
+    if (a_mn && !b_mn) return launch_gemm<true, false, BN>(gp, grid, stream);
+    return launch_gemm<true, true, BN>(gp, grid, stream);
+}
+
+}  // namespace pk
+
+extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
+    using namespace pk;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    PK_CHECK_ARG(d != nullptr, "null descriptor");
+    PK_CHECK_ARG(d->n_pairs >= 1 && d->n_pairs <= PK_GEMM_MAX_PAIRS, "n_pairs out of range");
+    PK_CHECK_ARG(d->kz_count >= 1, "kz_count must be >= 1");
+    PK_CHECK_ARG(d->c_dtype == PK_F32 || d->c_dtype == PK_BF16, "bad c_dtype");
+    PK_CHECK_ARG(!d->c_accumulate || d->c_dtype == PK_F32, "c_accumulate needs an f32 C");
+    PK_CHECK_ARG(d->drop_p >= 0.f && d->drop_p < 1.f, "drop_p out of range");
+    const long long N = d->c.dim[0], M = d->c.dim[1];
+    PK_CHECK_ARG(M > 0 && N > 0, "empty C");
+    int bn = d->block_n;
+    if (bn == 0) bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    PK_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "block_n must be 64, 128 or 256");
+
+    static thread_local GemmParams gp;   // ~2.6 KB; filled per call, copied into the launch
+    memset(&gp, 0, sizeof(gp));
+    long long K = d->a_mn_major ? d->a[0].dim[1] : d->a[0].dim[0];
+    for (int i = 0; i < d->n_pairs; ++i) {
+        const long long ka = d->a_mn_major ? d->a[i].dim[1] : d->a[i].dim[0];
+        const long long kb = d->b_mn_major ? d->b[i].dim[1] : d->b[i].dim[0];
+        PK_CHECK_ARG(ka == K && kb == K, "all pairs must share the reduction extent K");
+        int rc = make_map(&gp.a[i], d->a[i], 0, 64, d->a_mn_major ? 64 : BM, "A");
+        if (rc) return rc;
+        rc = make_map(&gp.b[i], d->b[i], 0, 64, d->b_mn_major ? 64 : bn, "B");
+        if (rc) return rc;
+        gp.a_off[i] = d->a_row_off[i];
+        gp.b_off[i] = d->b_row_off[i];
+    }
+    {
+        int rc = make_map(&gp.c, d->c, d->c_dtype == PK_F32, d->c_dtype == PK_F32 ? 32 : 64, BM, "C");
+        if (rc) return rc;
+    }
+    gp.n_pairs = d->n_pairs;
+    gp.kz_count = d->kz_count;
+    gp.num_k_blocks = (int)((K + BK - 1) / BK);
+    gp.M = (int)M;
+    gp.N = (int)N;
+    gp.tiles_m = (int)((M + BM - 1) / BM);
+    gp.tiles_n = (int)((N + bn - 1) / bn);
+    gp.zb0 = (int)d->c.dim[2];
+    gp.zb1 = (int)d->c.dim[3];
+    gp.a_sel2 = d->a_sel2; gp.a_sel3 = d->a_sel3; gp.b_sel2 = d->b_sel2; gp.b_sel3 = d->b_sel3;
+    gp.c_is_f32 = d->c_dtype == PK_F32;
+    gp.c_accumulate = d->c_accumulate;
+    gp.alpha = d->alpha;
+    gp.bias = d->bias;
+    gp.act = d->act;
+    if (d->drop_p > 0.f) {
+        double t = (double)d->drop_p * 4294967296.0;
+        gp.drop_thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+        if (gp.drop_thresh == 0) gp.drop_thresh = 1;
+        gp.drop_scale = 1.f / (1.f - d->drop_p);
+    }
+    gp.drop_seed = d->drop_seed;
+    gp.aux_mode = d->aux ? d->aux_mode : PK_AUX_NONE;
+    gp.aux_is_f32 = d->aux_dtype == PK_F32;
+    gp.aux = d->aux;
+    gp.aux_sm = d->aux_stride[0]; gp.aux_s0 = d->aux_stride[1]; gp.aux_s1 = d->aux_stride[2];
+    gp.aux_scale = d->aux_scale;
+
+    const long long num_tiles = (long long)gp.tiles_m * gp.tiles_n * gp.zb0 * gp.zb1;
+    PK_CHECK_ARG(num_tiles < (1ll << 31), "too many tiles");
+    int grid = num_sms();
+    if (num_tiles < grid) grid = (int)num_tiles;
+    if (bn == 64) return dispatch_major<64>(gp, d->a_mn_major, d->b_mn_major, grid, stream);
+    if (bn == 128) return dispatch_major<128>(gp, d->a_mn_major, d->b_mn_major, grid, stream);
+    return dispatch_major<256>(gp, d->a_mn_major, d->b_mn_major, grid, stream);
+}

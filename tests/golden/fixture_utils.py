@@ -1,0 +1,25 @@
+"""Deterministic weight tweaks shared by make_golden.py (applied to the REFERENCE model) and the
+parity tests (applied to the drop-in model).  Works on any module exposing the reference's
+attribute names (encoder.fc_out, embed, decoder, fc1, fc_gate, fc2)."""
+import torch
+
+
+def decode_fixture_reinit(m, blank_bias=4.0, s_l=0.15, s_j=0.05, s_o=0.1, enc_scale=8.0, seed=2024):
+    """A randomly initialised transducer never emits blank and its prediction net barely reacts to
+    its input, which makes beam search degenerate.  Re-draw the prediction
+    net / joint weights from wider seeded normals and bias blank so that hypotheses mix blanks,
+    repeated and distinct tokens, pruning and both termination rules."""
+    gg = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        m.encoder.fc_out.weight *= enc_scale
+        m.embed.weight.normal_(0, 1, generator=gg)
+        for n, p in m.decoder.named_parameters():
+            if "weight" in n:
+                p.normal_(0, s_l, generator=gg)
+            else:
+                p.zero_()
+        for l in (m.fc1, m.fc_gate):
+            l.weight.normal_(0, s_j, generator=gg)
+        m.fc2.weight.normal_(0, s_o, generator=gg)
+        m.fc2.bias[0] += blank_bias
+    return m

@@ -1,0 +1,248 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures by EXECUTING THE REFERENCE's own Python modules
+(imported from /root/reference through tests/golden/ref_shim.py) plus the two independent
+third-party stand-ins for its un-vendored dependencies (torchaudio rnnt_loss / kaldi fbank).
+
+Run in the build container only:   python tests/golden/make_golden.py
+Outputs: tests/golden/*.npz (small; committed).  The GPU box never runs this script.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+torch.set_num_threads(8)
+
+
+def disable_dropout(model):
+    """Parity fixtures run with dropout disabled (Philox streams cannot be reproduced by a custom
+    kernel) while BatchNorm stays in train mode -- SURVEY.md section 7 'Dropout parity'."""
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model.decoder.dropout = 0.0
+
+
+def build_ref_model(V, seed=777, embd=100):
+    from trainer.model.transducer import Net
+    torch.manual_seed(seed)                       # trainer/train_transducer_bmuf_otfaug.py:295
+    return Net(ref_shim.model_args(V, embd_dim=embd), 240, V)
+
+
+def weight_fingerprint(model):
+    out = {}
+    for k, v in model.state_dict().items():
+        if v.dtype.is_floating_point:
+            out[k] = np.array([v.double().sum().item(), v.double().abs().sum().item(),
+                               float(v.flatten()[0]), float(v.flatten()[-1])])
+    return out
+
+
+def ref_forward_cpu(m, x, y, softmax):
+    """trainer/model/transducer.py:88-111 with the hard-coded SOS.cuda() (:91) left out."""
+    enc = m.encoder(x)
+    sos = torch.zeros(y.shape[0], 1).long()
+    yy = torch.cat((sos, y), dim=1)
+    pred, _ = m.decoder(m.embed(yy))
+    T, U = enc.size(1), pred.size(1)
+    xe = enc.unsqueeze(2).expand(-1, -1, U, -1)
+    ye = pred.unsqueeze(1).expand(-1, T, -1, -1)
+    out = torch.cat((xe, ye), dim=-1)
+    out = m.fc2(torch.tanh(m.fc1(out)) * torch.sigmoid(m.fc_gate(out)))
+    if softmax:
+        out = F.log_softmax(out, dim=-1)
+    return enc, pred, out
+
+
+def golden_model():
+    """Reference model forward + (torchaudio-loss) backward on a small seeded batch."""
+    import torchaudio
+    V, B, T, U = 40, 2, 120, 6
+    m = build_ref_model(V)
+    fp = weight_fingerprint(m)
+    m.train()
+    disable_dropout(m)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(B, T, 240, generator=g)
+    y = torch.randint(1, V, (B, U), generator=g)
+    lens = torch.tensor([T, T - 17], dtype=torch.int32)
+    ulens = torch.tensor([U, U - 2], dtype=torch.int32)
+    # intermediate activations via forward hooks
+    taps = {}
+    hooks = []
+    for i in range(9):
+        hooks.append(m.encoder.hidden_bn[i].register_forward_hook(
+            lambda mod, inp, out, i=i: taps.__setitem__("tdnn%d" % i, out.detach().transpose(1, 2))))
+    for i in range(3):
+        hooks.append(m.encoder.transformer[i].register_forward_hook(
+            lambda mod, inp, out, i=i: taps.__setitem__("xf%d" % i, out.detach())))
+    enc, pred, logits = ref_forward_cpu(m, x, y, softmax=False)
+    for h in hooks:
+        h.remove()
+    lp = F.log_softmax(logits, -1)
+    tl = (lens - 42)
+    tl = tl // 4 + (tl % 4 != 0).int()            # trainer/train_transducer_bmuf_otfaug.py:79-82
+    costs = torchaudio.functional.rnnt_loss(lp, y.int(), tl, ulens, blank=0, reduction="none",
+                                            fused_log_softmax=False)
+    loss = costs.sum()
+    loss.backward()
+    out = dict(x=x.numpy(), y=y.numpy().astype(np.int32), lens=lens.numpy(), ulens=ulens.numpy(),
+               tlens=tl.numpy(), enc=enc.detach().numpy(), pred=pred.detach().numpy(),
+               logits=logits.detach().numpy(), costs=costs.detach().numpy(), V=np.array(V))
+    for k, v in taps.items():
+        out["tap_" + k] = v[:, ::7, ::13].contiguous().numpy()      # strided sample keeps the file small
+    for k, v in fp.items():
+        out["w_" + k] = v
+    for k, p in m.named_parameters():
+        gr = p.grad
+        out["g_" + k] = np.concatenate([[gr.double().norm().item(), gr.double().abs().max().item()],
+                                        gr.flatten()[:6].double().numpy()])
+    # BatchNorm running stats after one train-mode forward
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            out["bn_" + k] = np.array([v.double().sum().item(), float(v.flatten()[0])])
+    np.savez_compressed(os.path.join(HERE, "model_small.npz"), **out)
+    print("model_small: costs", costs.tolist(), "enc", tuple(enc.shape), "logits", tuple(logits.shape))
+
+
+def golden_encoder_eval():
+    """BASELINE config 1: encoder forward, 1 utterance, T=200, eval mode."""
+    m = build_ref_model(40)
+    m.eval()
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(1, 200, 240, generator=g)
+    with torch.no_grad():
+        enc = m.encoder(x)
+    np.savez_compressed(os.path.join(HERE, "encoder_eval_T200.npz"), x=x.numpy(), enc=enc.numpy())
+    print("encoder_eval_T200:", tuple(enc.shape))
+
+
+def golden_decode():
+    """Reference TransducerDecoder.decode_batch on CPU (beam search), eval mode."""
+    import types
+    ref_shim.load_beam_module()
+    from decoder.transducer_decoder import TransducerDecoder
+    import decoder.beam_transducer as bt
+    V = 40
+    m = build_ref_model(V)
+    m.eval()
+    from fixture_utils import decode_fixture_reinit
+    decode_fixture_reinit(m)          # see fixture_utils.py: random init decodes degenerately
+    g = torch.Generator().manual_seed(4321)
+    B, T = 3, 130
+    x = torch.randn(B, T, 240, generator=g)
+    x_len_frames = torch.tensor([130, 118, 101])
+    tl = x_len_frames - 42
+    tl = tl // 4 + (tl % 4 != 0).long()
+    cases = {}
+    for name, beam, nbest, prune in [("b4n1", 4, 1, True), ("b4n4np", 4, 4, False), ("b8n2", 8, 2, True)]:
+        dargs = types.SimpleNamespace(las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None,
+                                      nonblk_reward=0.0)
+        dec = TransducerDecoder(m, B, beam, n_best=nbest, blk=0, global_scorer=bt.GlobalScorer(),
+                                sm_scale=1.0, cuda=False, beam_prune=prune, args=dargs)
+        with torch.no_grad():
+            ret, enc = dec.decode_batch(x, tl, max_len=[int(t) + 100 for t in tl])
+        for b in range(B):
+            for n in range(nbest):
+                hyp = [int(t) for t in ret["predictions"][b][n]]
+                cases["%s_pred_%d_%d" % (name, b, n)] = np.array(hyp, np.int64)
+                cases["%s_score_%d_%d" % (name, b, n)] = np.array(float(ret["scores"][b][n]))
+        print("decode", name, [len(cases["%s_pred_%d_0" % (name, b)]) for b in range(B)],
+              [float(ret["scores"][b][0]) for b in range(B)])
+    np.savez_compressed(os.path.join(HERE, "decode_small.npz"), x=x.numpy(), tlens=tl.numpy(),
+                        enc=enc.numpy()[:, ::3, ::17], **cases)
+
+
+def golden_specaug():
+    """Reference SpecAugment (utils/spec_augment.py) with seeded torch + numpy RNGs."""
+    from utils.spec_augment import SpecAugment
+    out = {}
+    for i, seed in enumerate([0, 1, 7, 777]):
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        x = torch.ones(3, 200, 240)
+        sa = SpecAugment(15, 35)
+        sa.apply(x)
+        sa.apply(x)                                 # two consecutive draws from the same streams
+        out["mask_%d" % i] = np.packbits((x[0] == 0).numpy())
+        out["seed_%d" % i] = np.array(seed)
+    np.savez_compressed(os.path.join(HERE, "specaug.npz"), **out)
+    print("specaug done")
+
+
+def golden_frontend():
+    """AudioSegment hot methods from the reference (loader/audio.py), splice from
+    loader/otf_utt_loader.py, and torchaudio's Kaldi-compatible fbank as the PyKaldi stand-in."""
+    import torchaudio
+    from loader.audio import AudioSegment
+    from loader.otf_utt_loader import splice
+    rng = np.random.default_rng(5)
+    out = {}
+    n = 400 + 59 * 160 + 37
+    # speech-like: sum of a few sinusoids + noise, int16
+    t = np.arange(n) / 16000.0
+    wav = 3000 * np.sin(2 * np.pi * 220 * t) + 1500 * np.sin(2 * np.pi * 1330 * t + 1.0) + \
+        800 * rng.standard_normal(n)
+    pcm = np.clip(np.round(wav), -32768, 32767).astype(np.int16)
+    out["pcm"] = pcm
+    for rate, db in [(0.9, -23.5), (1.0, -41.0), (1.1, -12.25)]:
+        seg = AudioSegment(pcm, 16000)
+        seg.change_speed(rate)
+        seg.normalize(db)
+        aug = seg._convert_samples_from_float32(seg._samples, "int16")
+        key = "r%02d" % int(rate * 10)
+        out["aug_" + key] = aug
+        fb = torchaudio.compliance.kaldi.fbank(
+            torch.from_numpy(aug.astype(np.float32)).unsqueeze(0), num_mel_bins=80,
+            sample_frequency=16000.0, dither=0.0, low_freq=40.0, high_freq=-200.0,
+            window_type="hamming", energy_floor=0.0)
+        out["fbank_" + key] = fb.numpy()
+        out["splice_" + key] = splice(fb.numpy(), 1, 1)[::5]
+    np.savez_compressed(os.path.join(HERE, "frontend.npz"), **out)
+    print("frontend done", {k: v.shape for k, v in out.items() if k.startswith("fbank")})
+
+
+def golden_rnnt():
+    """torchaudio rnnt_loss (independent implementation) on seeded cases incl. ragged lengths."""
+    import torchaudio
+    out = {}
+    for i, (B, T, U, V) in enumerate([(1, 1, 0, 5), (2, 4, 3, 7), (3, 25, 9, 33), (4, 40, 17, 129)]):
+        g = torch.Generator().manual_seed(100 + i)
+        logits = 2.0 * torch.randn(B, T, U + 1, V, generator=g)
+        labels = torch.randint(1, V, (B, max(U, 1)), generator=g).int()[:, :U]
+        fl = torch.randint(max(1, T // 2), T + 1, (B,), generator=g).int()
+        ll = torch.randint(U // 2, U + 1, (B,), generator=g).int()
+        fl[0], ll[0] = T, U
+        lp = F.log_softmax(logits, -1).requires_grad_(True)
+        lab = labels if U > 0 else torch.zeros(B, 0, dtype=torch.int32)
+        if U == 0:
+            # torchaudio needs U>=1 storage; T=1,U=0 closed form: cost = -lp[0,0,blank]
+            costs = -lp[:, 0, 0, 0]
+        else:
+            costs = torchaudio.functional.rnnt_loss(lp, lab, fl, ll, blank=0, reduction="none",
+                                                    fused_log_softmax=False)
+        costs.sum().backward()
+        out["logits_%d" % i] = logits.numpy()
+        out["labels_%d" % i] = lab.numpy()
+        out["fl_%d" % i] = fl.numpy()
+        out["ll_%d" % i] = ll.numpy()
+        out["costs_%d" % i] = costs.detach().numpy()
+        out["grads_%d" % i] = lp.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "rnnt_loss.npz"), **out)
+    print("rnnt done")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["rnnt", "frontend", "specaug", "encoder", "model", "decode"]
+    table = dict(rnnt=golden_rnnt, frontend=golden_frontend, specaug=golden_specaug,
+                 encoder=golden_encoder_eval, model=golden_model, decode=golden_decode)
+    for w in which:
+        table[w]()
