@@ -90,6 +90,24 @@ typedef struct {
 
 int pk_gemm_bf16(const pk_gemm_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * RNN-T loss + gradient, fused with the log-softmax over V.
+ * Replaces F.log_softmax (trainer/model/transducer.py:110-111) + warp_rnnt RNNTLoss.apply
+ * (trainer/train_transducer_bmuf_otfaug.py:58,97-99; trainer/train_transducer_mbr_bmuf_otfaug.py:157-160)
+ * and autograd's backward through both.
+ *   logits  [B, T, U1, ldv] (first V of each row valid), dtype f32 | bf16, blank = 0
+ *   labels  [B, ld_labels] int32; frame_lens, label_lens [B] int32 (T_n <= T, U_n <= U1-1)
+ *   grad_scale [B] or NULL (dLoss/dcost_n, 1 when NULL)
+ *   costs   [B] f32 = -log P(y_n | x_n)
+ *   dlogits same shape/dtype as logits, may alias it (in place); NULL = loss only.
+ *           Entries of padded nodes and of the row padding [V, ldv) are written as 0.
+ */
+long long pk_rnnt_loss_workspace_bytes(int B, int T, int U1);
+int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const int* frame_lens,
+                         const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
+                         const float* grad_scale, float* costs, void* dlogits, void* workspace,
+                         long long workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -326,7 +326,7 @@ static int make_map(CUtensorMap* out, const pk_view4& v, int is_f32, int box0, i
     }
     for (int i = 0; i < 3; ++i) {
         long long sb = (long long)v.stride[i] * es;
-        if (v.dim[i + 1] == 1 && sb <= 0) sb = 16;       // unused dimension: any legal stride
+        if (v.dim[i + 1] == 1 && (sb <= 0 || (sb % 16) != 0)) sb = 16;   // unused dimension: any legal stride
         if (sb <= 0 || (sb % 16) != 0) {
             set_last_error("gemm %s: stride[%d]=%lld elements is not a positive multiple of 16 bytes", what, i,
                            (long long)v.stride[i]);

@@ -1,0 +1,343 @@
+// RNN-T loss (alpha/beta lattice) + gradient w.r.t. the joint logits, fused with log-softmax.
+//
+// Replaces  F.log_softmax (trainer/model/transducer.py:110-111)  +  warp_rnnt.RNNTLoss.apply
+// (trainer/train_transducer_bmuf_otfaug.py:58,97-99) and their autograd backward.
+//
+//   pass 1  rnnt_rowstats   one warp per joint node (b,t,u): streams the V logits once (16-byte
+//                           coalesced loads, several in flight per lane), online log-sum-exp ->
+//                           lse[b,t,u], lp_blank, lp_label written in a diagonal-major ("skewed")
+//                           layout so that pass 2 reads each anti-diagonal contiguously.
+//   pass 2  rnnt_lattice    one CTA per utterance: warp 0 runs the alpha wavefront, warp 1 the beta
+//                           wavefront (anti-diagonal sweep, previous diagonal staged in shared
+//                           memory, next diagonal's log-probs prefetched); then both warps emit the
+//                           per-node gradient coefficients.  Never touches the V axis.
+//   pass 3  rnnt_grad       one warp per node: re-reads the logits row and writes
+//                           dlogits = -softmax * (gb + gl) + [v==blank] gb + [v==label] gl
+//                           (in place if dlogits aliases logits).
+// Algorithmic HBM traffic: 3 * B*T*(U+1)*V * sizeof(elem)  (+ O(nodes) fp32).
+#include "../../include/pika_b200.h"
+#include "common.cuh"
+
+namespace pk {
+void count_launch();
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+template <typename T> struct Vec16;
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int N = 8;
+    PK_DEVICE static void unpack(const uint4& q, float (&f)[8]) {
+        f[0] = bf16lo(q.x); f[1] = bf16hi(q.x); f[2] = bf16lo(q.y); f[3] = bf16hi(q.y);
+        f[4] = bf16lo(q.z); f[5] = bf16hi(q.z); f[6] = bf16lo(q.w); f[7] = bf16hi(q.w);
+    }
+    PK_DEVICE static uint4 pack(const float (&f)[8]) {
+        return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+};
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    PK_DEVICE static void unpack(const uint4& q, float (&f)[4]) {
+        f[0] = __uint_as_float(q.x); f[1] = __uint_as_float(q.y); f[2] = __uint_as_float(q.z); f[3] = __uint_as_float(q.w);
+    }
+    PK_DEVICE static uint4 pack(const float (&f)[4]) {
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+};
+
+PK_DEVICE uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+PK_DEVICE uint4 ld_plain(const uint4* p) { return *p; }
+PK_DEVICE void st_stream(uint4* p, const uint4& v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct RnntDims {
+    int B, T, U1, V, ldv;     // padded batch dims; ldv = row pitch of logits in elements
+    int ld_labels;
+    int ND;                   // T + U1 - 1 diagonals
+};
+PK_DEVICE size_t skew_index(const RnntDims& d, int b, int t, int u) { return ((size_t)b * d.ND + (t + u)) * d.U1 + u; }
+
+constexpr int ROWSTATS_UNROLL = 4;
+
+// ------------------------------------------------------------------------------------ pass 1
+template <typename T>
+__global__ void __launch_bounds__(256) rnnt_rowstats_kernel(const T* __restrict__ logits, const int* __restrict__ labels,
+                                                            const int* __restrict__ frame_lens, const int* __restrict__ label_lens,
+                                                            RnntDims d, float* __restrict__ lse_out, float* __restrict__ lpb_skew,
+                                                            float* __restrict__ lpl_skew) {
+    constexpr int VN = Vec16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long rows = (long long)d.B * d.T * d.U1;
+    const int nvec = (d.V + VN - 1) / VN;
+    for (long long row = warp_global; row < rows; row += n_warps) {
+        const int u = (int)(row % d.U1);
+        const long long bt = row / d.U1;
+        const int t = (int)(bt % d.T);
+        const int b = (int)(bt / d.T);
+        const int Tn = frame_lens[b], Un = label_lens[b];
+        if (t >= Tn || u > Un) continue;       // padded node: never read (warp-uniform)
+        const T* rp = logits + row * (long long)d.ldv;
+        const uint4* vp = reinterpret_cast<const uint4*>(rp);
+        float m = -INFINITY, s = 0.f;          // running max (in log2 units) and sum of 2^(x*log2e - m)
+        for (int i0 = lane; i0 < nvec; i0 += 32 * ROWSTATS_UNROLL) {
+            uint4 q[ROWSTATS_UNROLL];
+#pragma unroll
+            for (int k = 0; k < ROWSTATS_UNROLL; ++k) {
+                const int i = i0 + k * 32;
+                if (i < nvec) q[k] = ld_stream(vp + i);
+            }
+#pragma unroll
+            for (int k = 0; k < ROWSTATS_UNROLL; ++k) {
+                const int i = i0 + k * 32;
+                if (i < nvec) {
+                    float f[VN];
+                    Vec16<T>::unpack(q[k], f);
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) {
+                        f[e] = (i * VN + e < d.V) ? f[e] * kLog2e : -INFINITY;
+                        cm = fmaxf(cm, f[e]);
+                    }
+                    if (cm > m) { s *= exp2f(m - cm); m = cm; }   // rare after the first chunks
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) s += exp2f(f[e] - m);
+                }
+            }
+        }
+        // combine the 32 lane-local (m, s) pairs
+        const float mw = warp_max(m);
+        s = (m == -INFINITY) ? 0.f : s * exp2f(m - mw);
+        s = warp_sum(s);
+        if (lane == 0) {
+            const float lse = (mw + log2f(s)) * kLn2;
+            const float zb = to_f32<T>(rp[0]);
+            lse_out[row] = lse;
+            const size_t sk = skew_index(d, b, t, u);
+            lpb_skew[sk] = zb - lse;
+            if (u < Un) {
+                const int y = labels[(size_t)b * d.ld_labels + u];
+                lpl_skew[sk] = to_f32<T>(rp[y]) - lse;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ pass 2
+PK_DEVICE float lse2(float a, float b) {
+    const float mx = fmaxf(a, b), mn = fminf(a, b);
+    if (mx == -INFINITY) return -INFINITY;
+    return mx + log1pf(__expf(mn - mx));
+}
+
+__global__ void __launch_bounds__(64) rnnt_lattice_kernel(const int* __restrict__ frame_lens, const int* __restrict__ label_lens,
+                                                          RnntDims d, const float* __restrict__ lpb_skew,
+                                                          const float* __restrict__ lpl_skew, float* __restrict__ alpha_skew,
+                                                          float* __restrict__ beta_skew, const float* __restrict__ grad_scale,
+                                                          float* __restrict__ costs, float* __restrict__ gb_out,
+                                                          float* __restrict__ gl_out) {
+    extern __shared__ float sm[];            // 2 warps x 2 diagonals x (U1 + 1)
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = frame_lens[b], U = label_lens[b];
+    const int W = d.U1 + 1;
+    float* buf0 = sm + warp * 2 * W;
+    float* buf1 = buf0 + W;
+    __shared__ float s_ll;
+    const size_t base = (size_t)b * d.ND * d.U1;
+    const bool valid = (T > 0 && T <= d.T && U >= 0 && U < d.U1);
+    if (valid) {
+        for (int i = lane; i < W; i += 32) { buf0[i] = -INFINITY; buf1[i] = -INFINITY; }
+        __syncwarp();
+        const int last = T - 1 + U;           // last diagonal
+        if (warp == 0) {
+            // ---------------- alpha: diagonals ascending
+            float* prev = buf0;
+            float* cur = buf1;
+            if (lane == 0) { cur[0] = 0.f; alpha_skew[base] = 0.f; }
+            __syncwarp();
+            for (int dg = 1; dg <= last; ++dg) {
+                float* tsw = prev; prev = cur; cur = tsw;
+                const int lo = max(0, dg - (T - 1)), hi = min(U, dg);
+                const size_t pbase = base + (size_t)(dg - 1) * d.U1;
+                for (int u = lo + lane; u <= hi; u += 32) {
+                    float a = -INFINITY, c = -INFINITY;
+                    if (u <= dg - 1) a = prev[u] + lpb_skew[pbase + u];              // from (t-1, u) via blank
+                    if (u >= 1) c = prev[u - 1] + lpl_skew[pbase + u - 1];          // from (t, u-1) via label u
+                    const float v = lse2(a, c);
+                    cur[u] = v;
+                    alpha_skew[base + (size_t)dg * d.U1 + u] = v;
+                }
+                __syncwarp();
+            }
+        } else {
+            // ---------------- beta: diagonals descending
+            float* prev = buf0;
+            float* cur = buf1;
+            if (lane == 0) {
+                const float v = lpb_skew[base + (size_t)last * d.U1 + U];
+                cur[U] = v;
+                beta_skew[base + (size_t)last * d.U1 + U] = v;
+            }
+            __syncwarp();
+            for (int dg = last - 1; dg >= 0; --dg) {
+                float* tsw = prev; prev = cur; cur = tsw;
+                const int lo = max(0, dg - (T - 1)), hi = min(U, dg);
+                const size_t cbase = base + (size_t)dg * d.U1;
+                for (int u = lo + lane; u <= hi; u += 32) {
+                    const int t = dg - u;
+                    float a = -INFINITY, c = -INFINITY;
+                    if (t + 1 <= T - 1) a = prev[u] + lpb_skew[cbase + u];           // to (t+1, u) via blank
+                    if (u + 1 <= U) c = prev[u + 1] + lpl_skew[cbase + u];           // to (t, u+1) via label u+1
+                    const float v = lse2(a, c);
+                    cur[u] = v;
+                    beta_skew[cbase + u] = v;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) { s_ll = cur[0]; costs[b] = -cur[0]; }
+        }
+    } else if (threadIdx.x == 0) {
+        costs[b] = 0.f;
+    }
+    __syncthreads();
+    // ---------------- per-node gradient coefficients (natural [b,t,u] layout); zero for padded nodes
+    const float gs = grad_scale ? grad_scale[b] : 1.f;
+    const float ll = valid ? s_ll : 0.f;
+    const int nodes = d.T * d.U1;
+    for (int i = threadIdx.x; i < nodes; i += blockDim.x) {
+        const int t = i / d.U1, u = i - t * d.U1;
+        float gb = 0.f, gl = 0.f;
+        if (valid && t < T && u <= U) {
+            const size_t sk = skew_index(d, b, t, u);
+            const float a = alpha_skew[sk];
+            float bn;
+            if (t < T - 1) bn = beta_skew[skew_index(d, b, t + 1, u)];
+            else bn = (u == U) ? 0.f : -INFINITY;
+            gb = -__expf(a + bn + lpb_skew[sk] - ll) * gs;
+            if (u < U) gl = -__expf(a + beta_skew[skew_index(d, b, t, u + 1)] + lpl_skew[sk] - ll) * gs;
+            if (!(gb == gb)) gb = 0.f;
+            if (!(gl == gl)) gl = 0.f;
+        }
+        gb_out[(size_t)b * nodes + i] = gb;
+        gl_out[(size_t)b * nodes + i] = gl;
+    }
+}
+
+// ------------------------------------------------------------------------------------ pass 3
+template <typename T>
+__global__ void __launch_bounds__(256) rnnt_grad_kernel(const T* logits, const int* __restrict__ labels,
+                                                        const int* __restrict__ label_lens, RnntDims d,
+                                                        const float* __restrict__ lse_in, const float* __restrict__ gb_in,
+                                                        const float* __restrict__ gl_in, T* dlogits) {
+    constexpr int VN = Vec16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long rows = (long long)d.B * d.T * d.U1;
+    const int nvec_ld = d.ldv / VN;            // also clears the row padding [V, ldv)
+    for (long long row = warp_global; row < rows; row += n_warps) {
+        const float gb = gb_in[row], gl = gl_in[row];
+        const uint4* vp = reinterpret_cast<const uint4*>(logits + row * (long long)d.ldv);
+        uint4* op = reinterpret_cast<uint4*>(dlogits + row * (long long)d.ldv);
+        if (gb == 0.f && gl == 0.f) {          // padded (or zero-probability) node: write zeros, read nothing
+            for (int i = lane; i < nvec_ld; i += 32) st_stream(op + i, make_uint4(0, 0, 0, 0));
+            continue;
+        }
+        const int u = (int)(row % d.U1);
+        const int b = (int)(row / ((long long)d.T * d.U1));
+        const int y = (u < label_lens[b]) ? labels[(size_t)b * d.ld_labels + u] : -1;
+        const float l2 = lse_in[row] * kLog2e;
+        const float gsum = -(gb + gl);          // softmax coefficient
+        for (int i0 = lane; i0 < nvec_ld; i0 += 32 * ROWSTATS_UNROLL) {
+            uint4 q[ROWSTATS_UNROLL];
+#pragma unroll
+            for (int k = 0; k < ROWSTATS_UNROLL; ++k) {
+                const int i = i0 + k * 32;
+                if (i < nvec_ld) q[k] = ld_plain(vp + i);
+            }
+#pragma unroll
+            for (int k = 0; k < ROWSTATS_UNROLL; ++k) {
+                const int i = i0 + k * 32;
+                if (i < nvec_ld) {
+                    float f[VN];
+                    Vec16<T>::unpack(q[k], f);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) {
+                        const int v = i * VN + e;
+                        float g = exp2f(f[e] * kLog2e - l2) * gsum;
+                        if (v == 0) g += gb;
+                        if (v == y) g += gl;
+                        f[e] = (v < d.V) ? g : 0.f;
+                    }
+                    st_stream(op + i, Vec16<T>::pack(f));
+                }
+            }
+        }
+    }
+}
+
+}  // namespace pk
+
+extern "C" long long pk_rnnt_loss_workspace_bytes(int B, int T, int U1) {
+    const long long nd = (long long)T + U1 - 1;
+    const long long skew = (long long)B * nd * U1;
+    const long long nodes = (long long)B * T * U1;
+    return (4 * skew + 3 * nodes) * 4 + 256;
+}
+
+extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const int* frame_lens,
+                                    const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
+                                    const float* grad_scale, float* costs, void* dlogits, void* workspace,
+                                    long long workspace_bytes, void* stream_v) {
+    using namespace pk;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    PK_CHECK_ARG(dtype == PK_F32 || dtype == PK_BF16, "bad dtype");
+    PK_CHECK_ARG(B > 0 && T > 0 && U1 > 0 && V > 1, "bad dims");
+    const int vn = dtype == PK_F32 ? 4 : 8;
+    PK_CHECK_ARG(ldv >= V && ldv % vn == 0, "ldv must be >= V and a multiple of 16 bytes");
+    PK_CHECK_ARG((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "logits not 16B aligned");
+    PK_CHECK_ARG(dlogits == nullptr || (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0, "dlogits not 16B aligned");
+    PK_CHECK_ARG(workspace_bytes >= pk_rnnt_loss_workspace_bytes(B, T, U1), "workspace too small");
+    PK_CHECK_ARG(2 * 2 * (U1 + 1) * 4 <= 200 * 1024, "U too large for the lattice kernel's shared memory");
+    RnntDims d{B, T, U1, V, ldv, ld_labels, T + U1 - 1};
+    const size_t skew = (size_t)B * d.ND * U1, nodes = (size_t)B * T * U1;
+    float* ws = reinterpret_cast<float*>(workspace);
+    float* lpb = ws; float* lpl = lpb + skew; float* alpha = lpl + skew; float* beta = alpha + skew;
+    float* lse = beta + skew; float* gb = lse + nodes; float* gl = gb + nodes;
+
+    const long long rows = (long long)nodes;
+    const int warps_per_cta = 8;
+    long long want = (rows + warps_per_cta - 1) / warps_per_cta;
+    const long long cap = (long long)num_sms() * 8 * 4;      // persistent grid-stride: 8 CTAs/SM x 4 waves
+    const int grid = (int)(want < cap ? want : cap);
+    if (dtype == PK_BF16)
+        rnnt_rowstats_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), labels,
+                                                                     frame_lens, label_lens, d, lse, lpb, lpl);
+    else
+        rnnt_rowstats_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(logits), labels, frame_lens,
+                                                              label_lens, d, lse, lpb, lpl);
+    PK_CHECK_LAUNCH(); count_launch();
+    const int lat_smem = 2 * 2 * (U1 + 1) * 4;
+    if (lat_smem > 48 * 1024)
+        PK_CHECK_CUDA(cudaFuncSetAttribute(rnnt_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lat_smem));
+    rnnt_lattice_kernel<<<B, 64, lat_smem, stream>>>(frame_lens, label_lens, d, lpb, lpl, alpha, beta, grad_scale, costs, gb, gl);
+    PK_CHECK_LAUNCH(); count_launch();
+    if (dlogits != nullptr) {
+        if (dtype == PK_BF16)
+            rnnt_grad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), labels,
+                                                                     label_lens, d, lse, gb, gl,
+                                                                     reinterpret_cast<__nv_bfloat16*>(dlogits));
+        else
+            rnnt_grad_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(logits), labels, label_lens, d,
+                                                              lse, gb, gl, reinterpret_cast<float*>(dlogits));
+        PK_CHECK_LAUNCH(); count_launch();
+    }
+    return 0;
+}

@@ -41,8 +41,9 @@ def test_cmvn_and_specaug():
     rng = np.random.default_rng(1)
     x = rng.standard_normal((2, 20, 240)).astype(np.float32)
     stats = np.zeros((2, 81))
-    stats[0, :80], stats[0, 80] = rng.standard_normal(80) * 100, 100.0
-    stats[1, :80] = (np.abs(rng.standard_normal(80)) + 2.0) * 100
+    mean, var, n = rng.standard_normal(80), np.abs(rng.standard_normal(80)) + 0.5, 100.0
+    stats[0, :80], stats[0, 80] = mean * n, n
+    stats[1, :80] = (var + mean * mean) * n
     off, sc = fe.cmvn_from_stats(stats)
     y = fe.apply_cmvn(x, off, sc, cmn=True)
     ref = (x - x.mean(1, keepdims=True) + off[None, None].astype(np.float32)) * sc[None, None].astype(np.float32)

