@@ -108,6 +108,73 @@ int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const
                          const float* grad_scale, float* costs, void* dlogits, void* workspace,
                          long long workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Memory-bound layers around the GEMMs (pika_b200/csrc/elementwise.cu).  `dtype` is the
+ * activation type (PK_BF16 production, PK_F32 fp32-class parity mode); statistics are f32.
+ */
+/* bf16 (hi) and optional residual (lo) copies of an f32/bf16 matrix, zero-padded to cols_pad:
+ * weight/activation staging for pk_gemm_bf16 (replaces the implicit casts of torch autocast-free fp32). */
+int pk_cast_split(const void* src, int src_dtype, long long ld_src, void* hi, void* lo, long long ld_dst,
+                  long long rows, int cols, int cols_pad, float scale, void* stream);
+/* nn.BatchNorm1d over rows [rows, C] (trainer/model/rnnt_tdnn_transformer.py:41,58-59,69,76-82,85):
+ * train: batch statistics incl. padded frames, running stats updated (momentum 0.1); eval: running stats.
+ * stats_ws: 2*C floats scratch.  mean/rstd [C] are saved for the backward. */
+int pk_bn_fwd(const void* x, void* y, int dtype, long long rows, int C, const float* w, const float* b, float eps,
+              int train, float momentum, float* run_mean, float* run_var, float* mean, float* rstd, float* stats_ws,
+              void* stream);
+/* BN backward; relu_mask=1 additionally multiplies by (x > 0): x is the BN input = ReLU output, so the
+ * result is the gradient w.r.t. the pre-ReLU TDNN/Linear output.  dw, db [C] are overwritten. */
+int pk_bn_bwd(const void* dy, const void* x, void* dx, int dtype, long long rows, int C, const float* w,
+              const float* mean, const float* rstd, int train, int relu_mask, float* dw, float* db, void* stream);
+/* out[c] = sum_r x[r,c]  (bias gradients) */
+int pk_colsum(const void* x, int dtype, long long rows, int C, float* out, void* stream);
+/* nn.LayerNorm(C, eps=1e-6) (trainer/model/modules/transformer.py:82, position_ffn.py:21) */
+int pk_layernorm_fwd(const void* x, void* y, int dtype, long long rows, int C, const float* w, const float* b, float eps,
+                     float* mean, float* rstd, void* stream);
+int pk_layernorm_bwd(const void* dy, const void* x, void* dx, int dtype, long long rows, int C, const float* w,
+                     const float* mean, const float* rstd, float* dw, float* db, void* stream);
+/* attention softmax over keys + dropout on the probabilities
+ * (trainer/model/modules/multi_headed_attn.py:220-221): S f32 [rows, ld_s] -> P, Pd=dropout(P) [rows, ld_p] */
+int pk_softmax_fwd(const float* S, long long ld_s, void* P, void* Pd, int dtype, long long ld_p, long long rows, int n,
+                   float drop_p, uint32_t seed, void* stream);
+int pk_softmax_bwd(const float* dPd, long long ld_d, const void* P, long long ld_p, void* dS, int dtype, long long rows,
+                   int n, float drop_p, uint32_t seed, void* stream);
+/* nn.Dropout with the counter-based RNG shared with the GEMM epilogue; mask_nz: dx = dy * (y != 0) * scale */
+int pk_dropout(const void* x, void* y, int dtype, long long n, float p, uint32_t seed, void* stream);
+int pk_mask_nz(const void* dy, const void* y, void* dx, int dtype, long long n, float scale, void* stream);
+int pk_add(const void* a, const void* b, void* o, int dtype, long long n, void* stream);
+/* F.log_softmax(scale * x) rows -> f32 (trainer/model/transducer.py:110-111; decoder/transducer_decoder.py:177) */
+int pk_log_softmax(const void* x, int dtype, long long ld, float* y, long long rows, int n, float scale, void* stream);
+/* gated joint, factored: h[b,t,u,:] = tanh(e1[b,t]+p1[b,u]) * sigmoid(eg[b,t]+pg[b,u])
+ * (trainer/model/transducer.py:102-108 without materialising the 2H-wide concat).
+ * ex [B*T, 2H], py [B*U1, 2H] = the x / y halves of fc1 | fc_gate applied to encoder / prediction outputs. */
+int pk_joint_gate_fwd(const void* ex, const void* py, void* h, int dtype, int B, int T, int U1, int H, void* stream);
+int pk_joint_gate_bwd(const void* ex, const void* py, const void* dh, void* dex, void* dpy, int dtype, int B, int T, int U1,
+                      int H, void* stream);
+/* one LSTM time step, pointwise part (nn.LSTM, gate order i,f,g,o; trainer/model/transducer.py:56-61) */
+int pk_lstm_cell_fwd(const float* gx, long long ld_gx, const float* gh, long long ld_gh, const float* c_prev, float* c_out,
+                     void* h_out, int dtype, long long ld_h, float* gates_save, int B, int H, void* stream);
+int pk_lstm_cell_bwd(const void* dh_out, long long ld_dho, const float* dh_rec, const float* dc_next, const float* gates,
+                     const float* c, const float* c_prev, void* dgates, int dtype, float* dc_prev, int B, int H, void* stream);
+/* nn.Embedding (trainer/model/transducer.py:52-53,94); rows padded to ld_out; padding_idx gets no gradient */
+int pk_embedding_fwd(const long long* idx, const float* table, int E, void* out, int dtype, int ld_out, long long n, void* stream);
+int pk_embedding_bwd(const long long* idx, const void* dout, int dtype, int ld, int E, float* dtable, long long n,
+                     long long padding_idx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser / BMUF on the flat fp32 parameter vector (pika_b200/csrc/optim.cu).
+ *   pk_absmax + pk_sgd_nesterov_clip: clip_grad_norm_(params, max_norm, inf) + optim.SGD(nesterov).step()
+ *                                     (trainer/train_transducer_bmuf_otfaug.py:53-55,105-110)
+ *   pk_bmuf_delta / pk_bmuf_update  : BmufTrainer.update_and_sync (trainer/bmuf.py:76-100); the sum over
+ *                                     ranks between the two is an NCCL all-reduce issued by the host side.
+ */
+int pk_absmax(const float* x, long long n, float* out, int* nan_flag, void* stream);
+int pk_sgd_nesterov_clip(float* p, const float* g, float* buf, long long n, float lr, float momentum, float max_norm,
+                         const float* absmax, int first, void* stream);
+int pk_bmuf_delta(const float* glob, const float* local, float* delta, long long n, void* stream);
+int pk_bmuf_update(float* glob, float* local, float* delta_prev, const float* delta_sum, long long n, int world,
+                   float block_momentum, float block_lr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

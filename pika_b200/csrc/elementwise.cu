@@ -1,0 +1,709 @@
+// Memory-bound kernels around the GEMMs: casts/splits, BatchNorm, LayerNorm, attention softmax,
+// dropout, column sums, gated joint, LSTM cell, embedding.  All are HBM-bound: 16-byte accesses,
+// threads along the contiguous channel axis, grids sized in multiples of the SM count.
+// Activations are templated on T = bf16 (production) | f32 (fp32-class parity mode).
+#include "../../include/pika_b200.h"
+#include "common.cuh"
+
+namespace pk {
+void count_launch();
+
+template <typename T> struct V8 {};   // 8 consecutive elements
+template <> struct V8<__nv_bfloat16> {
+    PK_DEVICE static void load(const __nv_bfloat16* p, float (&f)[8]) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        f[0] = bf16lo(q.x); f[1] = bf16hi(q.x); f[2] = bf16lo(q.y); f[3] = bf16hi(q.y);
+        f[4] = bf16lo(q.z); f[5] = bf16hi(q.z); f[6] = bf16lo(q.w); f[7] = bf16hi(q.w);
+    }
+    PK_DEVICE static void store(__nv_bfloat16* p, const float (&f)[8]) {
+        *reinterpret_cast<uint4*>(p) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+};
+template <> struct V8<float> {
+    PK_DEVICE static void load(const float* p, float (&f)[8]) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    PK_DEVICE static void store(float* p, const float (&f)[8]) {
+        *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+};
+
+static inline int grid_for(long long work_items, int per_cta, int waves = 8) {
+    long long g = (work_items + per_cta - 1) / per_cta;
+    long long cap = (long long)num_sms() * waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+#define PK_DISPATCH_T(dtype, ...)                                         \
+    if ((dtype) == PK_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }     \
+    else { using T = float; __VA_ARGS__; }
+
+// =============================================================================== cast / split
+// dst_hi[r, c] = bf16(scale * src[r, c]); dst_lo = bf16(scale*src - hi) (optional); columns
+// [cols, cols_pad) of dst are zero-filled.  src is f32 or bf16 (strided rows).
+template <typename S>
+__global__ void cast_split_kernel(const S* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long ld_dst, long long rows, int cols, int cols_pad,
+                                  float scale) {
+    const long long total = rows * cols_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols_pad;
+        const int c = (int)(i - r * cols_pad);
+        float v = 0.f;
+        if (c < cols) v = to_f32<S>(src[r * ld_src + c]) * scale;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[r * ld_dst + c] = h;
+        if (lo) lo[r * ld_dst + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// =============================================================================== column statistics
+// sums[c] += sum_r f(x[r,c]); sums2[c] += sum_r x[r,c]*g[r,c]  (g = x for BN stats, x_hat for BN/LN bwd)
+// Block: 128 threads x 8 channels = 1024 channels per pass; rows split across blockIdx.y.
+template <typename T, int MODE>   // MODE 0: (sum x, sum x^2); 1: (sum dy, sum dy*xhat) with xhat=(x-mean)*rstd
+__global__ void __launch_bounds__(128) colstats_kernel(const T* __restrict__ x, const T* __restrict__ aux, long long rows, int C,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       float* __restrict__ s1, float* __restrict__ s2) {
+    const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+    if (c0 >= C) return;
+    const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
+    const long long r0 = (long long)blockIdx.y * rows_per;
+    const long long r1 = min(rows, r0 + rows_per);
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float mu[8], rs[8];
+    if (MODE == 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { mu[e] = mean[c0 + e]; rs[e] = rstd[c0 + e]; }
+    }
+    for (long long r = r0; r < r1; ++r) {
+        float f[8];
+        V8<T>::load(x + r * C + c0, f);
+        if (MODE == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * f[e]; }
+        } else {
+            float g[8];
+            V8<T>::load(aux + r * C + c0, g);          // aux = BN input x; f = dy
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * (g[e] - mu[e]) * rs[e]; }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s1[c0 + e], a[e]);
+        if (s2) atomicAdd(&s2[c0 + e], b[e]);
+    }
+}
+
+// mean/rstd from (sum, sumsq); optional running-stat update (nn.BatchNorm1d, momentum 0.1, unbiased var)
+__global__ void bn_finalize_kernel(const float* __restrict__ s1, const float* __restrict__ s2, long long rows, int C, float eps,
+                                   float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ run_mean, float* __restrict__ run_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float n = (float)rows;
+    const float m = s1[c] / n;
+    float var = s2[c] / n - m * m;
+    var = fmaxf(var, 0.f);
+    mean[c] = m;
+    rstd[c] = rsqrtf(var + eps);
+    if (run_mean) {
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+        const float unb = rows > 1 ? var * n / (n - 1.f) : var;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * unb;
+    }
+}
+__global__ void bn_eval_stats_kernel(const float* __restrict__ run_mean, const float* __restrict__ run_var, int C, float eps,
+                                     float* __restrict__ mean, float* __restrict__ rstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = run_mean[c];
+    rstd[c] = rsqrtf(run_var[c] + eps);
+}
+
+// y = (x - mean) * rstd * w + b
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int C,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       const float* __restrict__ w, const float* __restrict__ b) {
+    const long long nvec = rows * C / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)((i * 8) % C);
+        float f[8];
+        V8<T>::load(x + i * 8, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float sc = rstd[c0 + e] * w[c0 + e];
+            f[e] = (f[e] - mean[c0 + e]) * sc + b[c0 + e];
+        }
+        V8<T>::store(y + i * 8, f);
+    }
+}
+
+// BN backward (train): dx = w*rstd*(dy - sdy/n - xhat*sdyx/n); optionally masked by relu_mask (x > 0,
+// x being the BN input = ReLU output, so this also back-propagates through the ReLU).
+// eval mode (sdy == nullptr): dx = w*rstd*dy.
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+                                                           long long rows, int C, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ w,
+                                                           const float* __restrict__ sdy, const float* __restrict__ sdyx,
+                                                           int relu_mask) {
+    const long long nvec = rows * C / 8;
+    const float inv_n = 1.f / (float)rows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)((i * 8) % C);
+        float g[8], f[8];
+        V8<T>::load(dy + i * 8, g);
+        V8<T>::load(x + i * 8, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = c0 + e;
+            const float xh = (f[e] - mean[c]) * rstd[c];
+            float d = g[e];
+            if (sdy) d = d - sdy[c] * inv_n - xh * sdyx[c] * inv_n;
+            d *= w[c] * rstd[c];
+            if (relu_mask && !(f[e] > 0.f)) d = 0.f;
+            g[e] = d;
+        }
+        V8<T>::store(dx + i * 8, g);
+    }
+}
+
+// =============================================================================== LayerNorm (C <= 8192, C % 8 == 0)
+// one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int C,
+                                                     const float* __restrict__ w, const float* __restrict__ b, float eps,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = warp; r < rows; r += nw) {
+        const T* xr = x + r * C;
+        float s = 0.f;
+        for (int c = lane * 8; c < C; c += 256) {
+            float f[8];
+            V8<T>::load(xr + c, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += f[e];
+        }
+        const float mu = warp_sum(s) / C;
+        float v = 0.f;
+        for (int c = lane * 8; c < C; c += 256) {
+            float f[8];
+            V8<T>::load(xr + c, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v += (f[e] - mu) * (f[e] - mu);
+        }
+        const float rs = rsqrtf(warp_sum(v) / C + eps);
+        for (int c = lane * 8; c < C; c += 256) {
+            float f[8];
+            V8<T>::load(xr + c, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = (f[e] - mu) * rs * w[c + e] + b[c + e];
+            V8<T>::store(y + r * C + c, f);
+        }
+        if (lane == 0 && mean_out) { mean_out[r] = mu; rstd_out[r] = rs; }
+    }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*w;  dw[c] += sum dy*xhat, db[c] += sum dy
+// Column sums: each lane keeps its own columns in registers across all rows of its warp (C <= 1024),
+// warps combine through shared memory, one global atomicAdd per column per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+                                                     long long rows, int C, const float* __restrict__ w,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     float* __restrict__ dw, float* __restrict__ db) {
+    extern __shared__ float sh[];       // dw_part[C], db_part[C]
+    float* dwp = sh;
+    float* dbp = sh + C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    float aw[4][8], ab[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { aw[k][e] = 0.f; ab[k][e] = 0.f; }
+    for (long long r = warp; r < rows; r += nw) {
+        const float mu = mean[r], rs = rstd[r];
+        float s1 = 0.f, s2 = 0.f;
+        float g[4][8], f[4][8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = lane * 8 + k * 256;
+            if (c < C) {
+                V8<T>::load(dy + r * C + c, g[k]);
+                V8<T>::load(x + r * C + c, f[k]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    f[k][e] = (f[k][e] - mu) * rs;              // xhat
+                    const float gw = g[k][e] * w[c + e];
+                    s1 += gw; s2 += gw * f[k][e];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / C; s2 = warp_sum(s2) / C;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = lane * 8 + k * 256;
+            if (c < C) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o[e] = rs * (g[k][e] * w[c + e] - s1 - f[k][e] * s2);
+                    aw[k][e] += g[k][e] * f[k][e];
+                    ab[k][e] += g[k][e];
+                }
+                V8<T>::store(dx + r * C + c, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = lane * 8 + k * 256;
+        if (c < C) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { atomicAdd(&dwp[c + e], aw[k][e]); atomicAdd(&dbp[c + e], ab[k][e]); }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        atomicAdd(&dw[i], dwp[i]);
+        atomicAdd(&db[i], dbp[i]);
+    }
+}
+
+// =============================================================================== attention softmax
+// S f32 [rows, ld_s] (first n valid) -> P (T) [rows, ld_p] and Pd = dropout(P); pad columns [n, ld_p) zeroed.
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, long long ld_s, T* __restrict__ P,
+                                                          T* __restrict__ Pd, long long ld_p, long long rows, int n,
+                                                          uint32_t drop_thresh, float drop_scale, uint32_t seed) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = warp; r < rows; r += nw) {
+        const float* sr = S + r * ld_s;
+        float m = -INFINITY;
+        for (int c = lane; c < n; c += 32) m = fmaxf(m, sr[c]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int c = lane; c < n; c += 32) s += __expf(sr[c] - m);
+        const float inv = 1.f / warp_sum(s);
+        for (int c = lane; c < (int)ld_p; c += 32) {
+            float p = 0.f;
+            if (c < n) p = __expf(sr[c] - m) * inv;
+            const T pt = from_f32<T>(p);
+            P[r * ld_p + c] = pt;
+            if (Pd != P) {
+                float pd = to_f32<T>(pt);
+                if (drop_thresh) pd = drop_keep((uint64_t)r * (uint64_t)n + c, seed, drop_thresh) ? pd * drop_scale : 0.f;
+                Pd[r * ld_p + c] = from_f32<T>(pd);
+            }
+        }
+    }
+}
+// dS[r,c] = P * (dP' - sum_c dP'*P), dP' = dPd * mask * scale; written as T with pad zeroed.
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ dPd, long long ld_d, const T* __restrict__ P,
+                                                          long long ld_p, T* __restrict__ dS, long long rows, int n,
+                                                          uint32_t drop_thresh, float drop_scale, uint32_t seed) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = warp; r < rows; r += nw) {
+        float dot = 0.f;
+        for (int c = lane; c < n; c += 32) {
+            float d = dPd[r * ld_d + c];
+            if (drop_thresh) d = drop_keep((uint64_t)r * (uint64_t)n + c, seed, drop_thresh) ? d * drop_scale : 0.f;
+            dot += d * to_f32<T>(P[r * ld_p + c]);
+        }
+        dot = warp_sum(dot);
+        for (int c = lane; c < (int)ld_p; c += 32) {
+            float o = 0.f;
+            if (c < n) {
+                float d = dPd[r * ld_d + c];
+                if (drop_thresh) d = drop_keep((uint64_t)r * (uint64_t)n + c, seed, drop_thresh) ? d * drop_scale : 0.f;
+                o = to_f32<T>(P[r * ld_p + c]) * (d - dot);
+            }
+            dS[r * ld_p + c] = from_f32<T>(o);
+        }
+    }
+}
+
+// =============================================================================== misc elementwise
+// y = dropout(x) with the GEMM epilogue's index convention (flat index of a contiguous tensor)
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, uint32_t thresh, float scale, uint32_t seed) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = to_f32<T>(x[i]);
+        y[i] = from_f32<T>(drop_keep((uint64_t)i, seed, thresh) ? v * scale : 0.f);
+    }
+}
+// dx = dy * (y != 0) * scale     (backward of ReLU and of ReLU+dropout given the saved output y)
+template <typename T>
+__global__ void mask_nz_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n, float scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = from_f32<T>(to_f32<T>(y[i]) != 0.f ? to_f32<T>(dy[i]) * scale : 0.f);
+}
+// out = a + b
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        o[i] = from_f32<T>(to_f32<T>(a[i]) + to_f32<T>(b[i]));
+}
+// log_softmax rows: x T [rows, ld] (first n valid) -> y f32 [rows, n] * 1
+template <typename T>
+__global__ void __launch_bounds__(256) log_softmax_kernel(const T* __restrict__ x, long long ld, float* __restrict__ y, long long rows,
+                                                          int n, float scale) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = warp; r < rows; r += nw) {
+        const T* xr = x + r * ld;
+        float m = -INFINITY;
+        for (int c = lane; c < n; c += 32) m = fmaxf(m, to_f32<T>(xr[c]) * scale);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int c = lane; c < n; c += 32) s += expf(to_f32<T>(xr[c]) * scale - m);
+        const float l = m + logf(warp_sum(s));
+        for (int c = lane; c < n; c += 32) y[r * n + c] = to_f32<T>(xr[c]) * scale - l;
+    }
+}
+
+// =============================================================================== gated joint
+// h[b,t,u,c] = tanh(e1[b,t,c] + p1[b,u,c]) * sigmoid(eg[b,t,c] + pg[b,u,c])
+// ex = [B*T, 2H] (cols [0,H) = fc1 part, [H,2H) = gate part), py = [B*U1, 2H]; biases already folded into ex.
+PK_DEVICE float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+template <typename T>
+__global__ void __launch_bounds__(128) joint_gate_fwd_kernel(const T* __restrict__ ex, const T* __restrict__ py, T* __restrict__ h,
+                                                             int B, int Tt, int U1, int H) {
+    // one CTA per (b,t); threads over channels (8 each); loop over u
+    const int bt = blockIdx.x;
+    const int b = bt / Tt;
+    for (int c0 = threadIdx.x * 8; c0 < H; c0 += blockDim.x * 8) {
+        float e1[8], eg[8];
+        V8<T>::load(ex + (long long)bt * 2 * H + c0, e1);
+        V8<T>::load(ex + (long long)bt * 2 * H + H + c0, eg);
+        for (int u = 0; u < U1; ++u) {
+            float p1[8], pg[8], o[8];
+            const T* pr = py + ((long long)b * U1 + u) * 2 * H;
+            V8<T>::load(pr + c0, p1);
+            V8<T>::load(pr + H + c0, pg);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = tanhf(e1[e] + p1[e]) * sigmoidf_(eg[e] + pg[e]);
+            V8<T>::store(h + ((long long)bt * U1 + u) * H + c0, o);
+        }
+    }
+}
+// backward, reduction over u:  dex[b,t,:] = sum_u (d1, dg);    d1 = dh*g*(1-a^2), dg = dh*a*g*(1-g)
+template <typename T>
+__global__ void __launch_bounds__(128) joint_gate_bwd_ex_kernel(const T* __restrict__ ex, const T* __restrict__ py,
+                                                                const T* __restrict__ dh, T* __restrict__ dex, int B, int Tt,
+                                                                int U1, int H) {
+    const int bt = blockIdx.x;
+    const int b = bt / Tt;
+    for (int c0 = threadIdx.x * 8; c0 < H; c0 += blockDim.x * 8) {
+        float e1[8], eg[8], a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ag[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        V8<T>::load(ex + (long long)bt * 2 * H + c0, e1);
+        V8<T>::load(ex + (long long)bt * 2 * H + H + c0, eg);
+        for (int u = 0; u < U1; ++u) {
+            float p1[8], pg[8], d[8];
+            const T* pr = py + ((long long)b * U1 + u) * 2 * H;
+            V8<T>::load(pr + c0, p1);
+            V8<T>::load(pr + H + c0, pg);
+            V8<T>::load(dh + ((long long)bt * U1 + u) * H + c0, d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float a = tanhf(e1[e] + p1[e]), g = sigmoidf_(eg[e] + pg[e]);
+                a1[e] += d[e] * g * (1.f - a * a);
+                ag[e] += d[e] * a * g * (1.f - g);
+            }
+        }
+        V8<T>::store(dex + (long long)bt * 2 * H + c0, a1);
+        V8<T>::store(dex + (long long)bt * 2 * H + H + c0, ag);
+    }
+}
+// backward, reduction over t: one CTA per (b,u)
+template <typename T>
+__global__ void __launch_bounds__(128) joint_gate_bwd_py_kernel(const T* __restrict__ ex, const T* __restrict__ py,
+                                                                const T* __restrict__ dh, T* __restrict__ dpy, int B, int Tt,
+                                                                int U1, int H) {
+    const int bu = blockIdx.x;
+    const int b = bu / U1, u = bu - b * U1;
+    for (int c0 = threadIdx.x * 8; c0 < H; c0 += blockDim.x * 8) {
+        float p1[8], pg[8], a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ag[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        V8<T>::load(py + (long long)bu * 2 * H + c0, p1);
+        V8<T>::load(py + (long long)bu * 2 * H + H + c0, pg);
+        for (int t = 0; t < Tt; ++t) {
+            float e1[8], eg[8], d[8];
+            const long long bt = (long long)b * Tt + t;
+            V8<T>::load(ex + bt * 2 * H + c0, e1);
+            V8<T>::load(ex + bt * 2 * H + H + c0, eg);
+            V8<T>::load(dh + (bt * U1 + u) * H + c0, d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float a = tanhf(e1[e] + p1[e]), g = sigmoidf_(eg[e] + pg[e]);
+                a1[e] += d[e] * g * (1.f - a * a);
+                ag[e] += d[e] * a * g * (1.f - g);
+            }
+        }
+        V8<T>::store(dpy + (long long)bu * 2 * H + c0, a1);
+        V8<T>::store(dpy + (long long)bu * 2 * H + H + c0, ag);
+    }
+}
+
+// =============================================================================== LSTM cell (gate order i,f,g,o)
+// gates = gx[b, :4H] + gh[b, :4H] (f32 both: gx holds W_ih x + b_ih + b_hh for this step)
+template <typename T>
+__global__ void lstm_cell_fwd_kernel(const float* __restrict__ gx, long long ld_gx, const float* __restrict__ gh, long long ld_gh,
+                                     const float* __restrict__ c_prev, float* __restrict__ c_out, T* __restrict__ h_out,
+                                     long long ld_h, float* __restrict__ gates_save, int B, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H) return;
+    const int b = i / H, j = i - b * H;
+    const float* a = gx + (long long)b * ld_gx;
+    float gi = a[j], gf = a[H + j], gg = a[2 * H + j], go = a[3 * H + j];
+    if (gh) {
+        const float* r = gh + (long long)b * ld_gh;
+        gi += r[j]; gf += r[H + j]; gg += r[2 * H + j]; go += r[3 * H + j];
+    }
+    gi = sigmoidf_(gi); gf = sigmoidf_(gf); gg = tanhf(gg); go = sigmoidf_(go);
+    const float cp = c_prev ? c_prev[i] : 0.f;
+    const float c = gf * cp + gi * gg;
+    c_out[i] = c;
+    h_out[(long long)b * ld_h + j] = from_f32<T>(go * tanhf(c));
+    if (gates_save) {
+        float* g = gates_save + (long long)b * 4 * H;
+        g[j] = gi; g[H + j] = gf; g[2 * H + j] = gg; g[3 * H + j] = go;
+    }
+}
+// dh_total = dh_out(t) + dh_rec; produces d(pre-activation gates) as T [B,4H] and dc_prev
+template <typename T>
+__global__ void lstm_cell_bwd_kernel(const T* __restrict__ dh_out, long long ld_dho, const float* __restrict__ dh_rec,
+                                     const float* __restrict__ dc_next, const float* __restrict__ gates, const float* __restrict__ c,
+                                     const float* __restrict__ c_prev, T* __restrict__ dgates, float* __restrict__ dc_prev, int B,
+                                     int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H) return;
+    const int b = i / H, j = i - b * H;
+    const float* g = gates + (long long)b * 4 * H;
+    const float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+    float dh = dh_out ? to_f32<T>(dh_out[(long long)b * ld_dho + j]) : 0.f;
+    if (dh_rec) dh += dh_rec[i];
+    const float tc = tanhf(c[i]);
+    float dc = dh * go * (1.f - tc * tc);
+    if (dc_next) dc += dc_next[i];
+    const float cp = c_prev ? c_prev[i] : 0.f;
+    T* d = dgates + (long long)b * 4 * H;
+    d[j] = from_f32<T>(dc * gg * gi * (1.f - gi));
+    d[H + j] = from_f32<T>(dc * cp * gf * (1.f - gf));
+    d[2 * H + j] = from_f32<T>(dc * gi * (1.f - gg * gg));
+    d[3 * H + j] = from_f32<T>(dh * tc * go * (1.f - go));
+    dc_prev[i] = dc * gf;
+}
+
+// =============================================================================== embedding
+template <typename T>
+__global__ void embedding_fwd_kernel(const long long* __restrict__ idx, const float* __restrict__ table, int E, T* __restrict__ out,
+                                     int ld_out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * ld_out; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / ld_out;
+        const int c = (int)(i - r * ld_out);
+        out[i] = from_f32<T>(c < E ? table[idx[r] * E + c] : 0.f);
+    }
+}
+template <typename T>
+__global__ void embedding_bwd_kernel(const long long* __restrict__ idx, const T* __restrict__ dout, int ld, int E,
+                                     float* __restrict__ dtable, long long n, long long padding_idx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * E; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / E;
+        const int c = (int)(i - r * E);
+        if (idx[r] != padding_idx) atomicAdd(&dtable[idx[r] * E + c], to_f32<T>(dout[r * ld + c]));
+    }
+}
+
+}  // namespace pk
+
+// ================================================================================================ C ABI
+using namespace pk;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define DONE() PK_CHECK_LAUNCH(); count_launch(); return 0
+
+static uint32_t drop_thresh_of(float p) {
+    if (p <= 0.f) return 0u;
+    double t = (double)p * 4294967296.0;
+    uint32_t r = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    return r == 0 ? 1u : r;
+}
+
+extern "C" int pk_cast_split(const void* src, int src_dtype, long long ld_src, void* hi, void* lo, long long ld_dst,
+                             long long rows, int cols, int cols_pad, float scale, void* stream) {
+    PK_CHECK_ARG(rows > 0 && cols > 0 && cols_pad >= cols, "bad shape");
+    const int grid = grid_for(rows * cols_pad, 256);
+    if (src_dtype == PK_F32)
+        cast_split_kernel<float><<<grid, 256, 0, STREAM(stream)>>>((const float*)src, ld_src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                                  ld_dst, rows, cols, cols_pad, scale);
+    else
+        cast_split_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)src, ld_src, (__nv_bfloat16*)hi,
+                                                                          (__nv_bfloat16*)lo, ld_dst, rows, cols, cols_pad, scale);
+    DONE();
+}
+
+/* BatchNorm1d over rows of x [rows, C].  stats_ws: 4*C floats (zeroed by the caller for train mode). */
+extern "C" int pk_bn_fwd(const void* x, void* y, int dtype, long long rows, int C, const float* w, const float* b, float eps,
+                         int train, float momentum, float* run_mean, float* run_var, float* mean, float* rstd, float* stats_ws,
+                         void* stream) {
+    PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
+    cudaStream_t st = STREAM(stream);
+    if (train) {
+        PK_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * C, st));
+        dim3 g((C / 8 + 127) / 128, (unsigned)grid_for(rows, 64, 4));
+        PK_DISPATCH_T(dtype, (colstats_kernel<T, 0><<<g, 128, 0, st>>>((const T*)x, nullptr, rows, C, nullptr, nullptr, stats_ws, stats_ws + C)));
+        PK_CHECK_LAUNCH(); count_launch();
+        bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(stats_ws, stats_ws + C, rows, C, eps, momentum, mean, rstd, run_mean, run_var);
+    } else {
+        bn_eval_stats_kernel<<<(C + 255) / 256, 256, 0, st>>>(run_mean, run_var, C, eps, mean, rstd);
+    }
+    PK_CHECK_LAUNCH(); count_launch();
+    const int grid = grid_for(rows * C / 8, 256);
+    PK_DISPATCH_T(dtype, (bn_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (T*)y, rows, C, mean, rstd, w, b)));
+    DONE();
+}
+
+/* dx (optionally ReLU-masked by x > 0), dw[C], db[C] (overwritten).  stats_ws: 2*C floats. */
+extern "C" int pk_bn_bwd(const void* dy, const void* x, void* dx, int dtype, long long rows, int C, const float* w,
+                         const float* mean, const float* rstd, int train, int relu_mask, float* dw, float* db, void* stream) {
+    PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
+    cudaStream_t st = STREAM(stream);
+    PK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
+    PK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C, st));
+    dim3 g((C / 8 + 127) / 128, (unsigned)grid_for(rows, 64, 4));
+    PK_DISPATCH_T(dtype, (colstats_kernel<T, 1><<<g, 128, 0, st>>>((const T*)dy, (const T*)x, rows, C, mean, rstd, db, dw)));
+    PK_CHECK_LAUNCH(); count_launch();
+    const int grid = grid_for(rows * C / 8, 256);
+    PK_DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, (T*)dx, rows, C, mean, rstd, w,
+                                                                       train ? db : nullptr, train ? dw : nullptr, relu_mask)));
+    DONE();
+}
+
+extern "C" int pk_colsum(const void* x, int dtype, long long rows, int C, float* out, void* stream) {
+    PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
+    cudaStream_t st = STREAM(stream);
+    PK_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+    dim3 g((C / 8 + 127) / 128, (unsigned)grid_for(rows, 64, 4));
+    PK_DISPATCH_T(dtype, (colstats_kernel<T, 0><<<g, 128, 0, st>>>((const T*)x, nullptr, rows, C, nullptr, nullptr, out, nullptr)));
+    DONE();
+}
+
+extern "C" int pk_layernorm_fwd(const void* x, void* y, int dtype, long long rows, int C, const float* w, const float* b, float eps,
+                                float* mean, float* rstd, void* stream) {
+    PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
+    const int grid = grid_for(rows, 8);
+    PK_DISPATCH_T(dtype, (ln_fwd_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)x, (T*)y, rows, C, w, b, eps, mean, rstd)));
+    DONE();
+}
+extern "C" int pk_layernorm_bwd(const void* dy, const void* x, void* dx, int dtype, long long rows, int C, const float* w,
+                                const float* mean, const float* rstd, float* dw, float* db, void* stream) {
+    PK_CHECK_ARG(C % 8 == 0 && rows > 0 && C <= 1024, "C must be a multiple of 8, <= 1024");
+    cudaStream_t st = STREAM(stream);
+    PK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C, st));
+    PK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
+    const int grid = grid_for(rows, 8, 2);
+    PK_DISPATCH_T(dtype, (ln_bwd_kernel<T><<<grid, 256, 2 * C * sizeof(float), st>>>((const T*)dy, (const T*)x, (T*)dx, rows, C, w, mean,
+                                                                                     rstd, dw, db)));
+    DONE();
+}
+
+extern "C" int pk_softmax_fwd(const float* S, long long ld_s, void* P, void* Pd, int dtype, long long ld_p, long long rows, int n,
+                              float drop_p, uint32_t seed, void* stream) {
+    PK_CHECK_ARG(rows > 0 && n > 0 && ld_p >= n && ld_s >= n, "bad shape");
+    const int grid = grid_for(rows, 8);
+    const uint32_t th = drop_thresh_of(drop_p);
+    const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed)));
+    DONE();
+}
+extern "C" int pk_softmax_bwd(const float* dPd, long long ld_d, const void* P, long long ld_p, void* dS, int dtype, long long rows,
+                              int n, float drop_p, uint32_t seed, void* stream) {
+    const int grid = grid_for(rows, 8);
+    const uint32_t th = drop_thresh_of(drop_p);
+    const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    PK_DISPATCH_T(dtype, (softmax_bwd_kernel<T><<<grid, 256, 0, STREAM(stream)>>>(dPd, ld_d, (const T*)P, ld_p, (T*)dS, rows, n, th, sc, seed)));
+    DONE();
+}
+
+extern "C" int pk_dropout(const void* x, void* y, int dtype, long long n, float p, uint32_t seed, void* stream) {
+    const int grid = grid_for(n, 1024);
+    const uint32_t th = drop_thresh_of(p);
+    PK_CHECK_ARG(th != 0, "p must be > 0");
+    PK_DISPATCH_T(dtype, (dropout_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)x, (T*)y, n, th, 1.f / (1.f - p), seed)));
+    DONE();
+}
+extern "C" int pk_mask_nz(const void* dy, const void* y, void* dx, int dtype, long long n, float scale, void* stream) {
+    const int grid = grid_for(n, 1024);
+    PK_DISPATCH_T(dtype, (mask_nz_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)dy, (const T*)y, (T*)dx, n, scale)));
+    DONE();
+}
+extern "C" int pk_add(const void* a, const void* b, void* o, int dtype, long long n, void* stream) {
+    const int grid = grid_for(n, 1024);
+    PK_DISPATCH_T(dtype, (add_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)a, (const T*)b, (T*)o, n)));
+    DONE();
+}
+extern "C" int pk_log_softmax(const void* x, int dtype, long long ld, float* y, long long rows, int n, float scale, void* stream) {
+    const int grid = grid_for(rows, 8);
+    PK_DISPATCH_T(dtype, (log_softmax_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)x, ld, y, rows, n, scale)));
+    DONE();
+}
+
+extern "C" int pk_joint_gate_fwd(const void* ex, const void* py, void* h, int dtype, int B, int T_, int U1, int H, void* stream) {
+    PK_CHECK_ARG(H % 8 == 0, "H must be a multiple of 8");
+    PK_DISPATCH_T(dtype, (joint_gate_fwd_kernel<T><<<B * T_, 128, 0, STREAM(stream)>>>((const T*)ex, (const T*)py, (T*)h, B, T_, U1, H)));
+    DONE();
+}
+extern "C" int pk_joint_gate_bwd(const void* ex, const void* py, const void* dh, void* dex, void* dpy, int dtype, int B, int T_, int U1,
+                                 int H, void* stream) {
+    PK_CHECK_ARG(H % 8 == 0, "H must be a multiple of 8");
+    PK_DISPATCH_T(dtype, (joint_gate_bwd_ex_kernel<T><<<B * T_, 128, 0, STREAM(stream)>>>((const T*)ex, (const T*)py, (const T*)dh, (T*)dex, B, T_, U1, H)));
+    PK_CHECK_LAUNCH(); count_launch();
+    PK_DISPATCH_T(dtype, (joint_gate_bwd_py_kernel<T><<<B * U1, 128, 0, STREAM(stream)>>>((const T*)ex, (const T*)py, (const T*)dh, (T*)dpy, B, T_, U1, H)));
+    DONE();
+}
+
+extern "C" int pk_lstm_cell_fwd(const float* gx, long long ld_gx, const float* gh, long long ld_gh, const float* c_prev, float* c_out,
+                                void* h_out, int dtype, long long ld_h, float* gates_save, int B, int H, void* stream) {
+    PK_DISPATCH_T(dtype, (lstm_cell_fwd_kernel<T><<<(B * H + 255) / 256, 256, 0, STREAM(stream)>>>(gx, ld_gx, gh, ld_gh, c_prev, c_out,
+                                                                                                (T*)h_out, ld_h, gates_save, B, H)));
+    DONE();
+}
+extern "C" int pk_lstm_cell_bwd(const void* dh_out, long long ld_dho, const float* dh_rec, const float* dc_next, const float* gates,
+                                const float* c, const float* c_prev, void* dgates, int dtype, float* dc_prev, int B, int H,
+                                void* stream) {
+    PK_DISPATCH_T(dtype, (lstm_cell_bwd_kernel<T><<<(B * H + 255) / 256, 256, 0, STREAM(stream)>>>((const T*)dh_out, ld_dho, dh_rec, dc_next,
+                                                                                                gates, c, c_prev, (T*)dgates, dc_prev, B, H)));
+    DONE();
+}
+
+extern "C" int pk_embedding_fwd(const long long* idx, const float* table, int E, void* out, int dtype, int ld_out, long long n,
+                                void* stream) {
+    const int grid = grid_for(n * ld_out, 256);
+    PK_DISPATCH_T(dtype, (embedding_fwd_kernel<T><<<grid, 256, 0, STREAM(stream)>>>(idx, table, E, (T*)out, ld_out, n)));
+    DONE();
+}
+extern "C" int pk_embedding_bwd(const long long* idx, const void* dout, int dtype, int ld, int E, float* dtable, long long n,
+                                long long padding_idx, void* stream) {
+    const int grid = grid_for(n * E, 256);
+    PK_DISPATCH_T(dtype, (embedding_bwd_kernel<T><<<grid, 256, 0, STREAM(stream)>>>(idx, (const T*)dout, ld, E, dtable, n, padding_idx)));
+    DONE();
+}

@@ -133,75 +133,129 @@ __global__ void __launch_bounds__(256) rnnt_rowstats_kernel(const T* __restrict_
 PK_DEVICE float lse2(float a, float b) {
     const float mx = fmaxf(a, b), mn = fminf(a, b);
     if (mx == -INFINITY) return -INFINITY;
-    return mx + log1pf(__expf(mn - mx));
+    return mx + log1pf(expf(mn - mx));
 }
 
-__global__ void __launch_bounds__(64) rnnt_lattice_kernel(const int* __restrict__ frame_lens, const int* __restrict__ label_lens,
-                                                          RnntDims d, const float* __restrict__ lpb_skew,
-                                                          const float* __restrict__ lpl_skew, float* __restrict__ alpha_skew,
-                                                          float* __restrict__ beta_skew, const float* __restrict__ grad_scale,
-                                                          float* __restrict__ costs, float* __restrict__ gb_out,
-                                                          float* __restrict__ gl_out) {
-    extern __shared__ float sm[];            // 2 warps x 2 diagonals x (U1 + 1)
+// One CTA per utterance, 2*G threads: threads [0,G) sweep alpha over ascending anti-diagonals,
+// threads [G,2G) sweep beta over descending ones; thread j owns label positions u = j, j+G, ...
+// The previous diagonal lives in shared memory (ping-pong), each group synchronises with its own
+// named barrier, and the log-probs of the NEXT diagonal are prefetched before the barrier so the
+// L2 latency overlaps the dependent LSE chain.
+constexpr int LAT_MAX_G = 512;
+constexpr int LAT_MAX_CPT = 4;      // cells per thread => U1 <= 2048
+
+__global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
+    const int* __restrict__ frame_lens, const int* __restrict__ label_lens, RnntDims d, int G, int cpt,
+    const float* __restrict__ lpb_skew, const float* __restrict__ lpl_skew, float* __restrict__ alpha_skew,
+    float* __restrict__ beta_skew, const float* __restrict__ grad_scale, float* __restrict__ costs,
+    float* __restrict__ gb_out, float* __restrict__ gl_out) {
+    extern __shared__ float sm[];            // 2 groups x 2 diagonals x (U1 + 2)
     const int b = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = threadIdx.x >= G ? 1 : 0;
+    const int j = threadIdx.x - grp * G;
     const int T = frame_lens[b], U = label_lens[b];
-    const int W = d.U1 + 1;
-    float* buf0 = sm + warp * 2 * W;
+    const int W = d.U1 + 2;
+    float* buf0 = sm + grp * 2 * W + 1;      // index -1 .. U1 valid
     float* buf1 = buf0 + W;
     __shared__ float s_ll;
     const size_t base = (size_t)b * d.ND * d.U1;
     const bool valid = (T > 0 && T <= d.T && U >= 0 && U < d.U1);
     if (valid) {
-        for (int i = lane; i < W; i += 32) { buf0[i] = -INFINITY; buf1[i] = -INFINITY; }
-        __syncwarp();
+        for (int i = j - 1; i <= d.U1; i += G) { buf0[i] = -INFINITY; buf1[i] = -INFINITY; }
+        named_bar_sync(1 + grp, G);
         const int last = T - 1 + U;           // last diagonal
-        if (warp == 0) {
+        if (grp == 0) {
             // ---------------- alpha: diagonals ascending
             float* prev = buf0;
             float* cur = buf1;
-            if (lane == 0) { cur[0] = 0.f; alpha_skew[base] = 0.f; }
-            __syncwarp();
+            if (j == 0) { cur[0] = 0.f; alpha_skew[base] = 0.f; }
+            float nb[LAT_MAX_CPT], nl[LAT_MAX_CPT];   // lpb(d-1,u), lpl(d-1,u-1) for the upcoming diagonal
+#pragma unroll
+            for (int c = 0; c < LAT_MAX_CPT; ++c) {
+                const int u = j + c * G;
+                nb[c] = (c < cpt && u <= U && last >= 1) ? lpb_skew[base + u] : 0.f;
+                nl[c] = (c < cpt && u >= 1 && u <= U && last >= 1) ? lpl_skew[base + u - 1] : 0.f;
+            }
+            named_bar_sync(1, G);
             for (int dg = 1; dg <= last; ++dg) {
                 float* tsw = prev; prev = cur; cur = tsw;
                 const int lo = max(0, dg - (T - 1)), hi = min(U, dg);
-                const size_t pbase = base + (size_t)(dg - 1) * d.U1;
-                for (int u = lo + lane; u <= hi; u += 32) {
-                    float a = -INFINITY, c = -INFINITY;
-                    if (u <= dg - 1) a = prev[u] + lpb_skew[pbase + u];              // from (t-1, u) via blank
-                    if (u >= 1) c = prev[u - 1] + lpl_skew[pbase + u - 1];          // from (t, u-1) via label u
-                    const float v = lse2(a, c);
-                    cur[u] = v;
-                    alpha_skew[base + (size_t)dg * d.U1 + u] = v;
+                float pb[LAT_MAX_CPT], pl[LAT_MAX_CPT];
+#pragma unroll
+                for (int c = 0; c < LAT_MAX_CPT; ++c) { pb[c] = nb[c]; pl[c] = nl[c]; }
+                if (dg < last) {                       // prefetch diagonal dg (used at dg+1)
+                    const size_t nbase = base + (size_t)dg * d.U1;
+#pragma unroll
+                    for (int c = 0; c < LAT_MAX_CPT; ++c) {
+                        const int u = j + c * G;
+                        if (c < cpt && u <= U) {
+                            nb[c] = lpb_skew[nbase + u];
+                            nl[c] = (u >= 1) ? lpl_skew[nbase + u - 1] : 0.f;
+                        }
+                    }
                 }
-                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < LAT_MAX_CPT; ++c) {
+                    const int u = j + c * G;
+                    if (c < cpt && u >= lo && u <= hi) {
+                        float a = -INFINITY, cc = -INFINITY;
+                        if (u <= dg - 1) a = prev[u] + pb[c];              // from (t-1, u) via blank
+                        if (u >= 1) cc = prev[u - 1] + pl[c];              // from (t, u-1) via label u
+                        const float v = lse2(a, cc);
+                        cur[u] = v;
+                        alpha_skew[base + (size_t)dg * d.U1 + u] = v;
+                    }
+                }
+                named_bar_sync(1, G);
             }
         } else {
             // ---------------- beta: diagonals descending
             float* prev = buf0;
             float* cur = buf1;
-            if (lane == 0) {
+            if (j == 0) {
                 const float v = lpb_skew[base + (size_t)last * d.U1 + U];
                 cur[U] = v;
                 beta_skew[base + (size_t)last * d.U1 + U] = v;
             }
-            __syncwarp();
+            float nb[LAT_MAX_CPT], nl[LAT_MAX_CPT];   // lpb(d,u), lpl(d,u) of the upcoming diagonal
+#pragma unroll
+            for (int c = 0; c < LAT_MAX_CPT; ++c) {
+                const int u = j + c * G;
+                const bool ok = c < cpt && u <= U && last >= 1;
+                nb[c] = ok ? lpb_skew[base + (size_t)(last - 1) * d.U1 + u] : 0.f;
+                nl[c] = ok ? lpl_skew[base + (size_t)(last - 1) * d.U1 + u] : 0.f;
+            }
+            named_bar_sync(2, G);
             for (int dg = last - 1; dg >= 0; --dg) {
                 float* tsw = prev; prev = cur; cur = tsw;
                 const int lo = max(0, dg - (T - 1)), hi = min(U, dg);
-                const size_t cbase = base + (size_t)dg * d.U1;
-                for (int u = lo + lane; u <= hi; u += 32) {
-                    const int t = dg - u;
-                    float a = -INFINITY, c = -INFINITY;
-                    if (t + 1 <= T - 1) a = prev[u] + lpb_skew[cbase + u];           // to (t+1, u) via blank
-                    if (u + 1 <= U) c = prev[u + 1] + lpl_skew[cbase + u];           // to (t, u+1) via label u+1
-                    const float v = lse2(a, c);
-                    cur[u] = v;
-                    beta_skew[cbase + u] = v;
+                float pb[LAT_MAX_CPT], pl[LAT_MAX_CPT];
+#pragma unroll
+                for (int c = 0; c < LAT_MAX_CPT; ++c) { pb[c] = nb[c]; pl[c] = nl[c]; }
+                if (dg > 0) {
+                    const size_t nbase = base + (size_t)(dg - 1) * d.U1;
+#pragma unroll
+                    for (int c = 0; c < LAT_MAX_CPT; ++c) {
+                        const int u = j + c * G;
+                        if (c < cpt && u <= U) { nb[c] = lpb_skew[nbase + u]; nl[c] = lpl_skew[nbase + u]; }
+                    }
                 }
-                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < LAT_MAX_CPT; ++c) {
+                    const int u = j + c * G;
+                    if (c < cpt && u >= lo && u <= hi) {
+                        const int t = dg - u;
+                        float a = -INFINITY, cc = -INFINITY;
+                        if (t + 1 <= T - 1) a = prev[u] + pb[c];            // to (t+1, u) via blank
+                        if (u + 1 <= U) cc = prev[u + 1] + pl[c];           // to (t, u+1) via label u+1
+                        const float v = lse2(a, cc);
+                        cur[u] = v;
+                        beta_skew[base + (size_t)dg * d.U1 + u] = v;
+                    }
+                }
+                named_bar_sync(2, G);
             }
-            if (lane == 0) { s_ll = cur[0]; costs[b] = -cur[0]; }
+            if (j == 0) { s_ll = cur[0]; costs[b] = -cur[0]; }
         }
     } else if (threadIdx.x == 0) {
         costs[b] = 0.f;
@@ -220,8 +274,8 @@ __global__ void __launch_bounds__(64) rnnt_lattice_kernel(const int* __restrict_
             float bn;
             if (t < T - 1) bn = beta_skew[skew_index(d, b, t + 1, u)];
             else bn = (u == U) ? 0.f : -INFINITY;
-            gb = -__expf(a + bn + lpb_skew[sk] - ll) * gs;
-            if (u < U) gl = -__expf(a + beta_skew[skew_index(d, b, t, u + 1)] + lpl_skew[sk] - ll) * gs;
+            gb = -expf(a + bn + lpb_skew[sk] - ll) * gs;
+            if (u < U) gl = -expf(a + beta_skew[skew_index(d, b, t, u + 1)] + lpl_skew[sk] - ll) * gs;
             if (!(gb == gb)) gb = 0.f;
             if (!(gl == gl)) gl = 0.f;
         }
@@ -305,7 +359,6 @@ extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* la
     PK_CHECK_ARG((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "logits not 16B aligned");
     PK_CHECK_ARG(dlogits == nullptr || (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0, "dlogits not 16B aligned");
     PK_CHECK_ARG(workspace_bytes >= pk_rnnt_loss_workspace_bytes(B, T, U1), "workspace too small");
-    PK_CHECK_ARG(2 * 2 * (U1 + 1) * 4 <= 200 * 1024, "U too large for the lattice kernel's shared memory");
     RnntDims d{B, T, U1, V, ldv, ld_labels, T + U1 - 1};
     const size_t skew = (size_t)B * d.ND * U1, nodes = (size_t)B * T * U1;
     float* ws = reinterpret_cast<float*>(workspace);
@@ -324,10 +377,13 @@ extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* la
         rnnt_rowstats_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(logits), labels, frame_lens,
                                                               label_lens, d, lse, lpb, lpl);
     PK_CHECK_LAUNCH(); count_launch();
-    const int lat_smem = 2 * 2 * (U1 + 1) * 4;
-    if (lat_smem > 48 * 1024)
-        PK_CHECK_CUDA(cudaFuncSetAttribute(rnnt_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lat_smem));
-    rnnt_lattice_kernel<<<B, 64, lat_smem, stream>>>(frame_lens, label_lens, d, lpb, lpl, alpha, beta, grad_scale, costs, gb, gl);
+    const int lat_smem = 2 * 2 * (U1 + 2) * 4;
+    int G = ((U1 + 31) / 32) * 32;
+    if (G > LAT_MAX_G) G = LAT_MAX_G;
+    const int cpt = (U1 + G - 1) / G;
+    PK_CHECK_ARG(cpt <= LAT_MAX_CPT, "U too large for the lattice kernel (U+1 <= 2048)");
+    rnnt_lattice_kernel<<<B, 2 * G, lat_smem, stream>>>(frame_lens, label_lens, d, G, cpt, lpb, lpl, alpha, beta, grad_scale,
+                                                     costs, gb, gl);
     PK_CHECK_LAUNCH(); count_launch();
     if (dlogits != nullptr) {
         if (dtype == PK_BF16)

