@@ -63,7 +63,7 @@ PK_DEVICE int pick_sel(int sel, int zb0, int zb1, int kz) {
     return sel == PK_SEL_ZB0 ? zb0 : (sel == PK_SEL_ZB1 ? zb1 : (sel == PK_SEL_KZ ? kz : 0));
 }
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, bool CF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -184,12 +184,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         }
     } else {
         // ===================================================== epilogue (warps 2..5)
+        // Compact loop over 16-byte output groups (8 bf16 / 4 f32 columns): one small tcgen05.ld per
+        // group keeps the body a few dozen instructions, so it stays resident in the instruction cache.
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;          // tile row owned by this thread
         const int et = threadIdx.x - 64;        // 0..127
         const bool store_thread = (et == 0);
-        const int CH = p.c_is_f32 ? 32 : 64;    // columns per 128-byte staging row
+        constexpr int GW = CF32 ? 4 : 8;        // columns per 16-byte group
+        constexpr int CH = 8 * GW;              // columns per 128-byte staging row
         uint8_t* cst = smem + Cfg::C_OFF;
+        const float relu_floor = (p.act == PK_ACT_RELU) ? 0.f : -INFINITY;
+        if (p.bias == nullptr) {
+            for (int j = et; j < BN; j += 128) bias_smem[j] = 0.f;
+            named_bar_sync(2, 128);
+        }
         int it = 0;
         uint32_t chunk_ctr = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -208,67 +216,72 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            const int n_chunks = BN / CH;
+            const bool row_ok = m < p.M;
+            const unsigned char* aux_row = nullptr;
+            if (p.aux_mode != PK_AUX_NONE && row_ok) {
+                const long long off = (long long)m * p.aux_sm + (long long)zb0 * p.aux_s0 + (long long)zb1 * p.aux_s1;
+                aux_row = reinterpret_cast<const unsigned char*>(p.aux) + off * (p.aux_is_f32 ? 4 : 2);
+            }
+            const uint64_t lin_row = ((uint64_t)(zb1 * p.zb0 + zb0) * (uint64_t)p.M + (uint64_t)m) * (uint64_t)p.N;
+            constexpr int n_chunks = BN / CH;
             for (int ch = 0; ch < n_chunks; ++ch) {
                 const int nc0 = n0 + ch * CH;
                 if (nc0 >= p.N) break;           // uniform across the 4 epilogue warps
-                uint32_t v[64];
-                {
-                    uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-                    tmem_ld_32x32(t_addr + ch * CH, v0);
-                    if (CH == 64) {
-                        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-                        tmem_ld_32x32(t_addr + ch * CH + 32, v1);
-                    }
-                    tmem_ld_wait();
-                }
-                // ---- fused epilogue on this thread's row segment
-                const bool row_ok = m < p.M;
-                const unsigned char* auxp = nullptr;
-                if (p.aux_mode != PK_AUX_NONE && row_ok) {
-                    long long off = (long long)m * p.aux_sm + (long long)zb0 * p.aux_s0 + (long long)zb1 * p.aux_s1 + nc0;
-                    auxp = reinterpret_cast<const unsigned char*>(p.aux) + off * (p.aux_is_f32 ? 4 : 2);
-                }
-                const uint64_t lin_row = ((uint64_t)(zb1 * p.zb0 + zb0) * (uint64_t)p.M + (uint64_t)m) * (uint64_t)p.N;
-#pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    if (j < CH) {
-                        float x = __uint_as_float(v[j]) * p.alpha;
-                        if (p.bias != nullptr) x += bias_smem[ch * CH + j];
-                        if (p.act == PK_ACT_RELU) x = fmaxf(x, 0.f);
-                        if (p.drop_thresh != 0u) {
-                            x = drop_keep(lin_row + (uint64_t)(nc0 + j), p.drop_seed, p.drop_thresh) ? x * p.drop_scale : 0.f;
-                        }
-                        if (auxp != nullptr && nc0 + j < p.N) {
-                            const float a = p.aux_is_f32 ? reinterpret_cast<const float*>(auxp)[j]
-                                                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(auxp)[j]);
-                            if (p.aux_mode == PK_AUX_ADD) x += a;
-                            else x = (a != 0.f) ? x * p.aux_scale : 0.f;
-                        }
-                        v[j] = __float_as_uint(x);
-                    }
-                }
-                // ---- stage into 128B-swizzled smem, then one thread issues the TMA store
                 uint8_t* sbuf = cst + (chunk_ctr & 1) * C_STAGE_BYTES;
                 if (store_thread) tma_store_wait_read<1>();     // the buffer used two chunks ago is free
                 named_bar_sync(1, 128);
                 uint8_t* srow = sbuf + row * 128;
-                if (p.c_is_f32) {
+#pragma unroll 2
+                for (int gq = 0; gq < 8; ++gq) {
+                    uint32_t rr[GW];
+                    if (CF32) tmem_ld_32x4(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[4]>(&rr[0]));
+                    else tmem_ld_32x8(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[8]>(&rr[0]));
+                    tmem_ld_wait();
+                    const int ncol = nc0 + gq * GW;
+                    float x[GW];
+                    const float* bsm = bias_smem + ch * CH + gq * GW;
 #pragma unroll
-                    for (int c16 = 0; c16 < 8; ++c16) {
-                        uint4 w = make_uint4(v[c16 * 4 + 0], v[c16 * 4 + 1], v[c16 * 4 + 2], v[c16 * 4 + 3]);
-                        *reinterpret_cast<uint4*>(srow + ((c16 ^ (row & 7)) << 4)) = w;
-                    }
-                } else {
+                    for (int e = 0; e < GW; ++e) x[e] = fmaxf(fmaf(__uint_as_float(rr[e]), p.alpha, bsm[e]), relu_floor);
+                    if (p.drop_thresh != 0u) {
 #pragma unroll
-                    for (int c16 = 0; c16 < 8; ++c16) {
-                        uint4 w;
-                        w.x = pack_bf16x2(__uint_as_float(v[c16 * 8 + 0]), __uint_as_float(v[c16 * 8 + 1]));
-                        w.y = pack_bf16x2(__uint_as_float(v[c16 * 8 + 2]), __uint_as_float(v[c16 * 8 + 3]));
-                        w.z = pack_bf16x2(__uint_as_float(v[c16 * 8 + 4]), __uint_as_float(v[c16 * 8 + 5]));
-                        w.w = pack_bf16x2(__uint_as_float(v[c16 * 8 + 6]), __uint_as_float(v[c16 * 8 + 7]));
-                        *reinterpret_cast<uint4*>(srow + ((c16 ^ (row & 7)) << 4)) = w;
+                        for (int e = 0; e < GW; ++e)
+                            x[e] = drop_keep(lin_row + (uint64_t)(ncol + e), p.drop_seed, p.drop_thresh) ? x[e] * p.drop_scale : 0.f;
                     }
+                    if (aux_row != nullptr && ncol < p.N) {       // N % GW == 0 is enforced on the host when aux is used
+                        float a[GW];
+                        if (p.aux_is_f32) {
+                            const float4* ap = reinterpret_cast<const float4*>(aux_row + (size_t)ncol * 4);
+#pragma unroll
+                            for (int e4 = 0; e4 < GW / 4; ++e4) {
+                                const float4 t4 = ap[e4];
+                                a[e4 * 4 + 0] = t4.x; a[e4 * 4 + 1] = t4.y; a[e4 * 4 + 2] = t4.z; a[e4 * 4 + 3] = t4.w;
+                            }
+                        } else {
+                            if (GW == 8) {
+                                const uint4 t4 = *reinterpret_cast<const uint4*>(aux_row + (size_t)ncol * 2);
+                                a[0] = bf16lo(t4.x); a[1] = bf16hi(t4.x); a[2] = bf16lo(t4.y); a[3] = bf16hi(t4.y);
+                                a[GW - 4] = bf16lo(t4.z); a[GW - 3] = bf16hi(t4.z); a[GW - 2] = bf16lo(t4.w); a[GW - 1] = bf16hi(t4.w);
+                            } else {
+                                const uint2 t2 = *reinterpret_cast<const uint2*>(aux_row + (size_t)ncol * 2);
+                                a[0] = bf16lo(t2.x); a[1] = bf16hi(t2.x); a[2] = bf16lo(t2.y); a[3] = bf16hi(t2.y);
+                            }
+                        }
+                        if (p.aux_mode == PK_AUX_ADD) {
+#pragma unroll
+                            for (int e = 0; e < GW; ++e) x[e] += a[e];
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < GW; ++e) x[e] = (a[e] != 0.f) ? x[e] * p.aux_scale : 0.f;
+                        }
+                    }
+                    uint4 w;
+                    if (CF32) {
+                        w = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+                    } else {
+                        w.x = pack_bf16x2(x[0], x[1]); w.y = pack_bf16x2(x[2], x[3]);
+                        w.z = pack_bf16x2(x[GW - 4], x[GW - 3]); w.w = pack_bf16x2(x[GW - 2], x[GW - 1]);
+                    }
+                    *reinterpret_cast<uint4*>(srow + ((gq ^ (row & 7)) << 4)) = w;
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, 128);
@@ -345,9 +358,9 @@ static int make_map(CUtensorMap* out, const pk_view4& v, int is_f32, int box0, i
 
 void count_launch();
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, bool CF32>
 static int launch_gemm(const GemmParams& gp, int grid, cudaStream_t stream) {
-    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN>;
+    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, CF32>;
     static bool configured = false;
     if (!configured) {
         PK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
@@ -361,10 +374,16 @@ static int launch_gemm(const GemmParams& gp, int grid, cudaStream_t stream) {
 
 template <int BN>
 static int dispatch_major(const GemmParams& gp, int a_mn, int b_mn, int grid, cudaStream_t stream) {
-    if (!a_mn && !b_mn) return launch_gemm<false, false, BN>(gp, grid, stream);
-    if (!a_mn && b_mn) return launch_gemm<false, true, BN>(gp, grid, stream);
-    if (a_mn && !b_mn) return launch_gemm<true, false, BN>(gp, grid, stream);
-    return launch_gemm<true, true, BN>(gp, grid, stream);
+    if (gp.c_is_f32) {
+        if (!a_mn && !b_mn) return launch_gemm<false, false, BN, true>(gp, grid, stream);
+        if (!a_mn && b_mn) return launch_gemm<false, true, BN, true>(gp, grid, stream);
+        if (a_mn && !b_mn) return launch_gemm<true, false, BN, true>(gp, grid, stream);
+        return launch_gemm<true, true, BN, true>(gp, grid, stream);
+    }
+    if (!a_mn && !b_mn) return launch_gemm<false, false, BN, false>(gp, grid, stream);
+    if (!a_mn && b_mn) return launch_gemm<false, true, BN, false>(gp, grid, stream);
+    if (a_mn && !b_mn) return launch_gemm<true, false, BN, false>(gp, grid, stream);
+    return launch_gemm<true, true, BN, false>(gp, grid, stream);
 }
 
 }  // namespace pk
@@ -380,6 +399,7 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
     PK_CHECK_ARG(d->drop_p >= 0.f && d->drop_p < 1.f, "drop_p out of range");
     const long long N = d->c.dim[0], M = d->c.dim[1];
     PK_CHECK_ARG(M > 0 && N > 0, "empty C");
+    PK_CHECK_ARG(d->aux == nullptr || d->aux_mode == PK_AUX_NONE || (N % 8 == 0), "aux epilogue needs N % 8 == 0");
     int bn = d->block_n;
     if (bn == 0) bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     PK_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "block_n must be 64, 128 or 256");

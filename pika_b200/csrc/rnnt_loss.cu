@@ -7,10 +7,10 @@
 //                           coalesced loads, several in flight per lane), online log-sum-exp ->
 //                           lse[b,t,u], lp_blank, lp_label written in a diagonal-major ("skewed")
 //                           layout so that pass 2 reads each anti-diagonal contiguously.
-//   pass 2  rnnt_lattice    one CTA per utterance: warp 0 runs the alpha wavefront, warp 1 the beta
-//                           wavefront (anti-diagonal sweep, previous diagonal staged in shared
-//                           memory, next diagonal's log-probs prefetched); then both warps emit the
-//                           per-node gradient coefficients.  Never touches the V axis.
+//   pass 2  rnnt_lattice    one CTA per utterance: one thread group sweeps alpha, a second one beta
+//                           (anti-diagonal wavefront, one lattice cell per thread, previous diagonal
+//                           staged in shared memory, next diagonal's log-probs prefetched, fp64);
+//                           then all threads emit the per-node gradient coefficients.  Never touches V.
 //   pass 3  rnnt_grad       one warp per node: re-reads the logits row and writes
 //                           dlogits = -softmax * (gb + gl) + [v==blank] gb + [v==label] gl
 //                           (in place if dlogits aliases logits).
@@ -130,10 +130,15 @@ __global__ void __launch_bounds__(256) rnnt_rowstats_kernel(const T* __restrict_
 }
 
 // ------------------------------------------------------------------------------------ pass 2
-PK_DEVICE float lse2(float a, float b) {
-    const float mx = fmaxf(a, b), mn = fminf(a, b);
-    if (mx == -INFINITY) return -INFINITY;
-    return mx + log1pf(expf(mn - mx));
+// The lattice runs in double precision: alpha/beta reach magnitudes of (T+U)*log V ~ 3000 where an
+// fp32 ulp (2.4e-4) would show up as a 1e-4-level relative error in the gradients.  The DP touches
+// only O(T*U) values per utterance, so fp64 costs nothing measurable next to the V-axis passes.
+typedef double lat_t;
+#define LAT_NEG_INF (-(double)INFINITY)
+PK_DEVICE lat_t lse2(lat_t a, lat_t b) {
+    const lat_t mx = fmax(a, b), mn = fmin(a, b);
+    if (mx == LAT_NEG_INF) return LAT_NEG_INF;
+    return mx + log1p(exp(mn - mx));
 }
 
 // One CTA per utterance, 2*G threads: threads [0,G) sweep alpha over ascending anti-diagonals,
@@ -146,29 +151,29 @@ constexpr int LAT_MAX_CPT = 4;      // cells per thread => U1 <= 2048
 
 __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
     const int* __restrict__ frame_lens, const int* __restrict__ label_lens, RnntDims d, int G, int cpt,
-    const float* __restrict__ lpb_skew, const float* __restrict__ lpl_skew, float* __restrict__ alpha_skew,
-    float* __restrict__ beta_skew, const float* __restrict__ grad_scale, float* __restrict__ costs,
+    const float* __restrict__ lpb_skew, const float* __restrict__ lpl_skew, lat_t* __restrict__ alpha_skew,
+    lat_t* __restrict__ beta_skew, const float* __restrict__ grad_scale, float* __restrict__ costs,
     float* __restrict__ gb_out, float* __restrict__ gl_out) {
-    extern __shared__ float sm[];            // 2 groups x 2 diagonals x (U1 + 2)
+    extern __shared__ lat_t sm[];            // 2 groups x 2 diagonals x (U1 + 2)
     const int b = blockIdx.x;
     const int grp = threadIdx.x >= G ? 1 : 0;
     const int j = threadIdx.x - grp * G;
     const int T = frame_lens[b], U = label_lens[b];
     const int W = d.U1 + 2;
-    float* buf0 = sm + grp * 2 * W + 1;      // index -1 .. U1 valid
-    float* buf1 = buf0 + W;
-    __shared__ float s_ll;
+    lat_t* buf0 = sm + grp * 2 * W + 1;      // index -1 .. U1 valid
+    lat_t* buf1 = buf0 + W;
+    __shared__ lat_t s_ll;
     const size_t base = (size_t)b * d.ND * d.U1;
     const bool valid = (T > 0 && T <= d.T && U >= 0 && U < d.U1);
     if (valid) {
-        for (int i = j - 1; i <= d.U1; i += G) { buf0[i] = -INFINITY; buf1[i] = -INFINITY; }
+        for (int i = j - 1; i <= d.U1; i += G) { buf0[i] = LAT_NEG_INF; buf1[i] = LAT_NEG_INF; }
         named_bar_sync(1 + grp, G);
         const int last = T - 1 + U;           // last diagonal
         if (grp == 0) {
             // ---------------- alpha: diagonals ascending
-            float* prev = buf0;
-            float* cur = buf1;
-            if (j == 0) { cur[0] = 0.f; alpha_skew[base] = 0.f; }
+            lat_t* prev = buf0;
+            lat_t* cur = buf1;
+            if (j == 0) { cur[0] = 0.0; alpha_skew[base] = 0.0; }
             float nb[LAT_MAX_CPT], nl[LAT_MAX_CPT];   // lpb(d-1,u), lpl(d-1,u-1) for the upcoming diagonal
 #pragma unroll
             for (int c = 0; c < LAT_MAX_CPT; ++c) {
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
             }
             named_bar_sync(1, G);
             for (int dg = 1; dg <= last; ++dg) {
-                float* tsw = prev; prev = cur; cur = tsw;
+                lat_t* tsw = prev; prev = cur; cur = tsw;
                 const int lo = max(0, dg - (T - 1)), hi = min(U, dg);
                 float pb[LAT_MAX_CPT], pl[LAT_MAX_CPT];
 #pragma unroll
@@ -198,10 +203,10 @@ __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
                 for (int c = 0; c < LAT_MAX_CPT; ++c) {
                     const int u = j + c * G;
                     if (c < cpt && u >= lo && u <= hi) {
-                        float a = -INFINITY, cc = -INFINITY;
+                        lat_t a = LAT_NEG_INF, cc = LAT_NEG_INF;
                         if (u <= dg - 1) a = prev[u] + pb[c];              // from (t-1, u) via blank
                         if (u >= 1) cc = prev[u - 1] + pl[c];              // from (t, u-1) via label u
-                        const float v = lse2(a, cc);
+                        const lat_t v = lse2(a, cc);
                         cur[u] = v;
                         alpha_skew[base + (size_t)dg * d.U1 + u] = v;
                     }
@@ -210,10 +215,10 @@ __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
             }
         } else {
             // ---------------- beta: diagonals descending
-            float* prev = buf0;
-            float* cur = buf1;
+            lat_t* prev = buf0;
+            lat_t* cur = buf1;
             if (j == 0) {
-                const float v = lpb_skew[base + (size_t)last * d.U1 + U];
+                const lat_t v = lpb_skew[base + (size_t)last * d.U1 + U];
                 cur[U] = v;
                 beta_skew[base + (size_t)last * d.U1 + U] = v;
             }
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
             }
             named_bar_sync(2, G);
             for (int dg = last - 1; dg >= 0; --dg) {
-                float* tsw = prev; prev = cur; cur = tsw;
+                lat_t* tsw = prev; prev = cur; cur = tsw;
                 const int lo = max(0, dg - (T - 1)), hi = min(U, dg);
                 float pb[LAT_MAX_CPT], pl[LAT_MAX_CPT];
 #pragma unroll
@@ -245,17 +250,17 @@ __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
                     const int u = j + c * G;
                     if (c < cpt && u >= lo && u <= hi) {
                         const int t = dg - u;
-                        float a = -INFINITY, cc = -INFINITY;
+                        lat_t a = LAT_NEG_INF, cc = LAT_NEG_INF;
                         if (t + 1 <= T - 1) a = prev[u] + pb[c];            // to (t+1, u) via blank
                         if (u + 1 <= U) cc = prev[u + 1] + pl[c];           // to (t, u+1) via label u+1
-                        const float v = lse2(a, cc);
+                        const lat_t v = lse2(a, cc);
                         cur[u] = v;
                         beta_skew[base + (size_t)dg * d.U1 + u] = v;
                     }
                 }
                 named_bar_sync(2, G);
             }
-            if (j == 0) { s_ll = cur[0]; costs[b] = -cur[0]; }
+            if (j == 0) { s_ll = cur[0]; costs[b] = (float)(-cur[0]); }
         }
     } else if (threadIdx.x == 0) {
         costs[b] = 0.f;
@@ -263,19 +268,19 @@ __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
     __syncthreads();
     // ---------------- per-node gradient coefficients (natural [b,t,u] layout); zero for padded nodes
     const float gs = grad_scale ? grad_scale[b] : 1.f;
-    const float ll = valid ? s_ll : 0.f;
+    const lat_t ll = valid ? s_ll : 0.0;
     const int nodes = d.T * d.U1;
     for (int i = threadIdx.x; i < nodes; i += blockDim.x) {
         const int t = i / d.U1, u = i - t * d.U1;
         float gb = 0.f, gl = 0.f;
         if (valid && t < T && u <= U) {
             const size_t sk = skew_index(d, b, t, u);
-            const float a = alpha_skew[sk];
-            float bn;
+            const lat_t a = alpha_skew[sk];
+            lat_t bn;
             if (t < T - 1) bn = beta_skew[skew_index(d, b, t + 1, u)];
-            else bn = (u == U) ? 0.f : -INFINITY;
-            gb = -expf(a + bn + lpb_skew[sk] - ll) * gs;
-            if (u < U) gl = -expf(a + beta_skew[skew_index(d, b, t, u + 1)] + lpl_skew[sk] - ll) * gs;
+            else bn = (u == U) ? 0.0 : LAT_NEG_INF;
+            gb = (float)(-exp(a + bn + (lat_t)lpb_skew[sk] - ll)) * gs;
+            if (u < U) gl = (float)(-exp(a + beta_skew[skew_index(d, b, t, u + 1)] + (lat_t)lpl_skew[sk] - ll)) * gs;
             if (!(gb == gb)) gb = 0.f;
             if (!(gl == gl)) gl = 0.f;
         }
@@ -343,7 +348,7 @@ extern "C" long long pk_rnnt_loss_workspace_bytes(int B, int T, int U1) {
     const long long nd = (long long)T + U1 - 1;
     const long long skew = (long long)B * nd * U1;
     const long long nodes = (long long)B * T * U1;
-    return (4 * skew + 3 * nodes) * 4 + 256;
+    return (2 * skew + 3 * nodes) * 4 + 2 * skew * 8 + 256;
 }
 
 extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const int* frame_lens,
@@ -361,9 +366,10 @@ extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* la
     PK_CHECK_ARG(workspace_bytes >= pk_rnnt_loss_workspace_bytes(B, T, U1), "workspace too small");
     RnntDims d{B, T, U1, V, ldv, ld_labels, T + U1 - 1};
     const size_t skew = (size_t)B * d.ND * U1, nodes = (size_t)B * T * U1;
-    float* ws = reinterpret_cast<float*>(workspace);
-    float* lpb = ws; float* lpl = lpb + skew; float* alpha = lpl + skew; float* beta = alpha + skew;
-    float* lse = beta + skew; float* gb = lse + nodes; float* gl = gb + nodes;
+    double* wsd = reinterpret_cast<double*>(workspace);          // doubles first (8-byte alignment)
+    double* alpha = wsd; double* beta = alpha + skew;
+    float* lpb = reinterpret_cast<float*>(beta + skew); float* lpl = lpb + skew;
+    float* lse = lpl + skew; float* gb = lse + nodes; float* gl = gb + nodes;
 
     const long long rows = (long long)nodes;
     const int warps_per_cta = 8;
@@ -377,7 +383,7 @@ extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* la
         rnnt_rowstats_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(logits), labels, frame_lens,
                                                               label_lens, d, lse, lpb, lpl);
     PK_CHECK_LAUNCH(); count_launch();
-    const int lat_smem = 2 * 2 * (U1 + 2) * 4;
+    const int lat_smem = 2 * 2 * (U1 + 2) * 8;
     int G = ((U1 + 31) / 32) * 32;
     if (G > LAT_MAX_G) G = LAT_MAX_G;
     const int cpt = (U1 + G - 1) / G;

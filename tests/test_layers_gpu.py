@@ -10,6 +10,10 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+# the torch references must be real fp32 (cuDNN convolutions default to TF32, whose 1e-3 error flips
+# ReLU masks at near-zero pre-activations)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def rel(a, b):
@@ -43,8 +47,10 @@ def test_linear_relu_residual():
     gx, gr, gw, gb = torch.autograd.grad(ref, [x, res, lin.weight, lin.bias], dy)
     lin.weight.grad = lin.bias.grad = None
     y.backward(dy)
-    assert rel(x.grad, gx) < TOL and rel(res.grad, gr) < TOL
-    assert rel(lin.weight.grad, gw) < TOL and rel(lin.bias.grad, gb) < TOL
+    assert rel(x.grad, gx) < TOL
+    assert rel(res.grad, gr) < TOL
+    assert rel(lin.weight.grad, gw) < TOL
+    assert rel(lin.bias.grad, gb) < TOL
     # relu variant
     x2 = g(100, 240, seed=4).requires_grad_(True)
     y2 = E.linear(x2, lin.weight, lin.bias, act=True)
@@ -54,7 +60,8 @@ def test_linear_relu_residual():
     gx2, gw2 = torch.autograd.grad(ref2, [x2, lin.weight], dy2)
     lin.weight.grad = None
     y2.backward(dy2)
-    assert rel(x2.grad, gx2) < TOL and rel(lin.weight.grad, gw2) < TOL
+    assert rel(x2.grad, gx2) < TOL
+    assert rel(lin.weight.grad, gw2) < TOL
 
 
 def test_linear_concatenated_qkv():
@@ -71,7 +78,8 @@ def test_linear_concatenated_qkv():
     y.backward(dy)
     assert rel(x.grad, gs[0]) < TOL
     for i, l in enumerate(ls):
-        assert rel(l.weight.grad, gs[1 + i]) < TOL and rel(l.bias.grad, gs[4 + i]) < TOL
+        assert rel(l.weight.grad, gs[1 + i]) < TOL
+        assert rel(l.bias.grad, gs[4 + i]) < TOL
 
 
 @pytest.mark.parametrize("dil,stride", [(1, 1), (3, 1), (3, 4)])
@@ -81,13 +89,16 @@ def test_tdnn(dil, stride):
     conv = nn.Conv2d(1, C, (3, C), dilation=(dil, 1), stride=(stride, 1)).cuda()
     x = g(3, 90, C, seed=8).requires_grad_(True)
     y = E.TdnnFn.apply(x, conv.weight, conv.bias, dil, stride)
-    ref = F.relu(conv(x.unsqueeze(1))).squeeze(-1).transpose(1, 2)
-    assert y.shape == ref.shape and rel(y, ref) < TOL
+    pre = conv(x.unsqueeze(1)).squeeze(-1).transpose(1, 2)
+    assert y.shape == pre.shape and rel(y, F.relu(pre)) < TOL
+    ref = pre * (y.detach() > 0)          # same ReLU mask on both sides (ties at |pre| ~ 1e-7 are arbitrary)
     dy = g(*ref.shape, seed=9)
     gx, gw, gb = torch.autograd.grad(ref, [x, conv.weight, conv.bias], dy)
     conv.weight.grad = conv.bias.grad = None
     y.backward(dy)
-    assert rel(x.grad, gx) < TOL and rel(conv.weight.grad, gw) < TOL and rel(conv.bias.grad, gb) < TOL
+    assert rel(x.grad, gx) < TOL
+    assert rel(conv.weight.grad, gw) < TOL
+    assert rel(conv.bias.grad, gb) < TOL
 
 
 @pytest.mark.parametrize("train", [True, False])
@@ -106,8 +117,11 @@ def test_batchnorm(train):
     dy = g(333, 256, seed=15)
     gx, gw, gb = torch.autograd.grad(ref, [x, ref_bn.weight, ref_bn.bias], dy)
     y.backward(dy)
-    assert rel(x.grad, gx) < TOL and rel(bn.weight.grad, gw) < TOL and rel(bn.bias.grad, gb) < TOL
-    assert rel(bn.running_mean, ref_bn.running_mean) < 1e-4 and rel(bn.running_var, ref_bn.running_var) < 1e-4
+    assert rel(x.grad, gx) < TOL
+    assert rel(bn.weight.grad, gw) < TOL
+    assert rel(bn.bias.grad, gb) < TOL
+    assert rel(bn.running_mean, ref_bn.running_mean) < 1e-4
+    assert rel(bn.running_var, ref_bn.running_var) < 1e-4
 
 
 def test_layernorm():
@@ -123,7 +137,9 @@ def test_layernorm():
     gx, gw, gb = torch.autograd.grad(ref, [x, ln.weight, ln.bias], dy)
     ln.weight.grad = ln.bias.grad = None
     y.backward(dy)
-    assert rel(x.grad, gx) < TOL and rel(ln.weight.grad, gw) < TOL and rel(ln.bias.grad, gb) < TOL
+    assert rel(x.grad, gx) < TOL
+    assert rel(ln.weight.grad, gw) < TOL
+    assert rel(ln.bias.grad, gb) < TOL
 
 
 @pytest.mark.parametrize("heads,T", [(4, 50), (2, 77)])
@@ -214,7 +230,7 @@ def test_joint_and_fused_loss():
     dy = torch.zeros_like(logits)
     dy[..., :V] = g(B, T, U + 1, V, seed=28)
     params = [enc, pred] + [p for l in (m.fc1, m.fc_gate, m.fc2) for p in l.parameters()]
-    gs = torch.autograd.grad(ref, params, dy[..., :V])
+    gs = torch.autograd.grad(ref, params, dy[..., :V], retain_graph=True)
     for p in params:
         p.grad = None
     logits.backward(dy)
