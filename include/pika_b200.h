@@ -175,6 +175,31 @@ int pk_bmuf_delta(const float* glob, const float* local, float* delta, long long
 int pk_bmuf_update(float* glob, float* local, float* delta_prev, const float* delta_sum, long long n, int world,
                    float block_momentum, float block_lr, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * On-the-fly front end (pika_b200/csrc/frontend.cu): int16 PCM -> speed perturbation + RMS gain +
+ * int16 re-quantisation -> Kaldi fbank -> splice -> last-frame padding -> CMN/CMVN -> SpecAugment.
+ * Replaces loader/audio.py (AudioSegment.change_speed/normalize/_convert_*), the PyKaldi
+ * Fbank.compute_features call and splice() in loader/otf_utt_loader.py:28-46,195-201,218-234,262-270,
+ * and trainer/train_transducer_bmuf_otfaug.py:86-93 + utils/spec_augment.py:10-20.
+ *   pcm [B, ld_pcm] int16; n_samples, new_len (= int(n/rate)), n_frames (= 1+(new_len-400)/160) [B] int32
+ *   rate, target_db [B] f32 (host-drawn, as the reference draws them in the loader thread)
+ *   window [400], twiddle [256 x (re,im)], mel_w [n_mel,256], mel_lo/hi [n_mel]: host-built tables
+ *   offset/scale [D] CMVN (NULL = off); cmn: subtract the per-utterance mean over the PADDED time axis
+ *   (f0,fs,t0,ts): SpecAugment freq/time mask start and span (span 0 = off), shared by the batch
+ *   out [B, t_max, D] f32|bf16; wave_i16_out [B, n_max] optional copy of the augmented samples
+ *   err_flag: set to 1 if a gain above 300 dB was requested (the reference raises ValueError)
+ */
+long long pk_frontend_workspace_bytes(int B, int n_max, int t_max, int n_mel, int D);
+int pk_frontend_fwd(const short* pcm, long long ld_pcm, const int* n_samples, const float* rate, const int* new_len,
+                    const float* target_db, const int* n_frames, int B, int n_max, int t_max, int n_mel, int lctx,
+                    int rctx, const float* window, const float* twiddle, const float* mel_w, const int* mel_lo,
+                    const int* mel_hi, float preemph, int cmn, const float* offset, const float* scale, int f0, int fs,
+                    int t0, int ts, void* out, int out_dtype, short* wave_i16_out, void* workspace,
+                    long long workspace_bytes, int* err_flag, void* stream);
+int pk_fbank(const float* wave, long long ld_wave, const int* n_frames, int B, int t_max, int n_mel, const float* window,
+             const float* twiddle, const float* mel_w, const int* mel_lo, const int* mel_hi, float preemph, float* feats,
+             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,52 @@
+"""One RNN-T training batch on the GPU -- the body of run_one_epoch's hot loop
+(trainer/train_transducer_bmuf_otfaug.py:71-130) with every numerically heavy stage replaced by the
+sm_100a kernels: H2D of raw PCM -> on-GPU augmentation + fbank + splice + CMN/CMVN + SpecAugment ->
+encoder / prediction net / fused joint+loss forward and backward -> inf-norm clip + Nesterov SGD ->
+BMUF block sync every ``sync_period`` batches.
+"""
+import torch
+
+from .. import engine
+from ..frontend import Frontend
+from .flat import FlatParams, SgdNesterovClip, lr_at
+from .bmuf import BmufTrainer, SUCCESS
+
+
+def encoder_out_lens(lens, lctx, rctx, stride):
+    """T' = ceil((T - lctx - rctx) / stride) (trainer/train_transducer_bmuf_otfaug.py:79-82)"""
+    l = lens - lctx - rctx
+    return l // stride + (l % stride != 0).to(l.dtype)
+
+
+class TrainStep:
+    def __init__(self, model, args, frontend, bmuf, optimizer, offset=None, scale=None, spec_augmentor=None):
+        self.model, self.args, self.frontend, self.bmuf, self.opt = model, args, frontend, bmuf, optimizer
+        self.offset, self.scale, self.spec = offset, scale, spec_augmentor
+        self.num_done = 0
+
+    def features(self, batch):
+        """batch: dict of device tensors (pcm int16 [B,n], n_samples, rate, target_db, new_len, n_frames) + t_max"""
+        a = self.args
+        sa = (0, 0, 0, 0)
+        if self.spec is not None:
+            sa = self.spec.draw(batch["t_max"], self.frontend.D)
+        return self.frontend(batch["pcm"], batch["n_samples"], batch["rate"], batch["target_db"], batch["new_len"],
+                             batch["n_frames"], batch["t_max"], out_dtype=engine.act_dtype(), cmn=bool(a.cmn),
+                             offset=self.offset, scale=self.scale, specaug=sa)
+
+    def __call__(self, batch):
+        """-> per-utterance costs [B] (device).  Mirrors :71-123 of the reference trainer."""
+        a = self.args
+        self.opt.flat.zero_grad()                                         # optimizer.zero_grad()
+        feats = self.features(batch)
+        len_batch = encoder_out_lens(batch["n_frames"], a.model_lctx, a.model_rctx, a.model_stride)
+        costs = engine.transducer_loss(self.model, feats, batch["target"], len_batch, batch["ali_lens"])
+        costs.sum().backward()
+        self.opt.step()                                                   # clip_grad_norm_(inf) + SGD(nesterov)
+        if self.num_done != 0 and self.num_done % a.sync_period == 0:
+            if self.bmuf.update_and_sync() != SUCCESS:
+                raise FloatingPointError("BMUF: non-finite block delta")
+            self.opt.reset(lr_at(a.initial_lr, a.final_lr, a.epoch * a.num_batches_per_epoch + self.num_done,
+                                 a.num_epochs * a.num_batches_per_epoch))
+        self.num_done += 1
+        return costs

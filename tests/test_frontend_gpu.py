@@ -1,0 +1,91 @@
+"""GPU parity of the on-the-fly front end against the fixtures produced by the reference's own
+AudioSegment / splice code and torchaudio's Kaldi fbank (tests/golden/frontend.npz), and against the
+numpy oracle for CMN/CMVN/SpecAugment and last-frame padding.  Integer path (augmented int16 samples):
+bit-exact for the speed-perturbed (float64) branch; <= 1 LSB on the rate == 1.0 (float32) branch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def make_frontend():
+    from pika_b200.frontend import FbankOptions, Frontend
+    opts = FbankOptions(num_mel_bins=80, low_freq=40.0, high_freq=-200.0, dither=0.0, window_type="hamming")
+    return Frontend(opts, 1, 1, "cuda")
+
+
+def run(fe, pcms, rates, dbs, **kw):
+    from pika_b200.frontend import Frontend
+    B = len(pcms)
+    n = [len(p) for p in pcms]
+    new_len, frames = Frontend.lengths(n, rates)
+    n_max = max(max(n), max(new_len))
+    pcm = torch.zeros(B, n_max, dtype=torch.int16)
+    for i, p in enumerate(pcms):
+        pcm[i, :len(p)] = torch.from_numpy(p)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device="cuda")
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32, device="cuda")
+    t_max = kw.pop("t_max", max(frames))
+    out, wave = fe(pcm.cuda(), i32(n), f32(rates), f32(dbs), i32(new_len), i32(frames), t_max, want_wave=True, **kw)
+    torch.cuda.synchronize()
+    return out.float().cpu().numpy(), wave.cpu().numpy(), new_len, frames
+
+
+def test_augment_fbank_splice_vs_reference_golden(golden_dir):
+    d = np.load(os.path.join(golden_dir, "frontend.npz"))
+    fe = make_frontend()
+    keys, rates, dbs = ["r09", "r10", "r11"], [0.9, 1.0, 1.1], [-23.5, -41.0, -12.25]
+    out, wave, new_len, frames = run(fe, [d["pcm"]] * 3, rates, dbs, cmn=False)
+    for i, k in enumerate(keys):
+        aug = d["aug_" + k]
+        assert new_len[i] == len(aug) and frames[i] == d["fbank_" + k].shape[0]
+        diff = np.abs(wave[i, :len(aug)].astype(np.int32) - aug.astype(np.int32))
+        if rates[i] == 1.0:
+            assert diff.max() <= 1 and (diff != 0).mean() < 5e-3     # float32 branch: see module docstring
+        else:
+            assert diff.max() == 0                                   # float64 branch: bit-exact
+        ref = d["splice_" + k]                                       # every 5th spliced frame
+        got = out[i, :frames[i]][::5]
+        np.testing.assert_allclose(got, ref, atol=5e-3)
+        assert np.abs(got - ref).mean() < 2e-4
+        # padding beyond the utterance replicates the last valid spliced frame (loader/otf_utt_loader.py:262-266)
+        if frames[i] < out.shape[1]:
+            np.testing.assert_array_equal(out[i, frames[i]:], np.broadcast_to(out[i, frames[i] - 1], out[i, frames[i]:].shape))
+
+
+def test_cmn_cmvn_specaug_vs_oracle(golden_dir):
+    from oracle import frontend as ofe
+    d = np.load(os.path.join(golden_dir, "frontend.npz"))
+    fe = make_frontend()
+    rng = np.random.default_rng(3)
+    pcm2 = np.clip(np.round(rng.normal(0, 2500, 400 + 160 * 39)), -32768, 32767).astype(np.int16)
+    pcms, rates, dbs = [d["pcm"], pcm2], [1.1, 0.9], [-20.0, -30.0]
+    raw, wave, new_len, frames = run(fe, pcms, rates, dbs, cmn=False)
+    stats = np.zeros((2, 81))
+    mean, var, n = rng.standard_normal(80) * 3 + 8, np.abs(rng.standard_normal(80)) + 1.0, 1000.0
+    stats[0, :80], stats[0, 80], stats[1, :80] = mean * n, n, (var + mean * mean) * n
+    off, sc = ofe.cmvn_from_stats(stats)
+    sa = (100, 9, 11, 17)
+    out, _, _, _ = run(fe, pcms, rates, dbs, cmn=True, offset=torch.tensor(off, dtype=torch.float32, device="cuda"),
+                       scale=torch.tensor(sc, dtype=torch.float32, device="cuda"), specaug=sa)
+    ref = ofe.spec_augment(ofe.apply_cmvn(raw, off, sc, cmn=True), *sa)
+    np.testing.assert_allclose(out, ref, atol=2e-4)
+    assert np.all(out[:, :, 100:109] == 0) and np.all(out[:, 11:28, :] == 0)
+    # oracle chain from the augmented samples (numpy Kaldi restatement)
+    fb = ofe.kaldi_fbank(wave[1, :new_len[1]].astype(np.float32))
+    np.testing.assert_allclose(raw[1, :frames[1]], ofe.splice(fb, 1, 1), atol=5e-3)
+
+
+def test_bf16_output_and_batch_of_full_length():
+    fe = make_frontend()
+    rng = np.random.default_rng(4)
+    n = 400 + 160 * 99
+    pcms = [np.clip(np.round(rng.normal(0, 3000, n)), -32768, 32767).astype(np.int16) for _ in range(4)]
+    o32, _, _, frames = run(fe, pcms, [1.0] * 4, [-25.0] * 4, cmn=True)
+    o16, _, _, _ = run(fe, pcms, [1.0] * 4, [-25.0] * 4, cmn=True, out_dtype=torch.bfloat16)
+    assert frames == [100] * 4 and o32.shape == (4, 100, 240)
+    np.testing.assert_allclose(o16, o32, atol=2e-2, rtol=1e-2)
+    assert abs(o32.mean(axis=1)).max() < 1e-4            # CMN: zero mean over time
