@@ -86,6 +86,7 @@ typedef struct {
     int64_t aux_stride[3];            /* strides of (m, zb0, zb1) in elements */
     float aux_scale;
     int block_n;                      /* 0 = auto; else 64 | 128 | 256 */
+    int k_splits;                     /* 0 = auto; 1 = off; >1 = split the reduction (plain f32 2-D C only) */
 } pk_gemm_desc;
 
 int pk_gemm_bf16(const pk_gemm_desc* desc, void* stream);
@@ -118,16 +119,18 @@ int pk_cast_split(const void* src, int src_dtype, long long ld_src, void* hi, vo
                   long long rows, int cols, int cols_pad, float scale, void* stream);
 /* nn.BatchNorm1d over rows [rows, C] (trainer/model/rnnt_tdnn_transformer.py:41,58-59,69,76-82,85):
  * train: batch statistics incl. padded frames, running stats updated (momentum 0.1); eval: running stats.
- * stats_ws: 2*C floats scratch.  mean/rstd [C] are saved for the backward. */
+ * stats_ws: pk_colstats_ws_floats(C) + 2*C floats scratch.  mean/rstd [C] are saved for the backward. */
+long long pk_colstats_ws_floats(int C);
 int pk_bn_fwd(const void* x, void* y, int dtype, long long rows, int C, const float* w, const float* b, float eps,
               int train, float momentum, float* run_mean, float* run_var, float* mean, float* rstd, float* stats_ws,
               void* stream);
 /* BN backward; relu_mask=1 additionally multiplies by (x > 0): x is the BN input = ReLU output, so the
  * result is the gradient w.r.t. the pre-ReLU TDNN/Linear output.  dw, db [C] are overwritten. */
 int pk_bn_bwd(const void* dy, const void* x, void* dx, int dtype, long long rows, int C, const float* w,
-              const float* mean, const float* rstd, int train, int relu_mask, float* dw, float* db, void* stream);
-/* out[c] = sum_r x[r,c]  (bias gradients) */
-int pk_colsum(const void* x, int dtype, long long rows, int C, float* out, void* stream);
+              const float* mean, const float* rstd, int train, int relu_mask, float* dw, float* db, float* ws /* pk_colstats_ws_floats(C) */,
+              void* stream);
+/* out[c] = sum_r x[r,c]  (bias gradients); ws: pk_colstats_ws_floats(C) floats */
+int pk_colsum(const void* x, int dtype, long long rows, int C, float* out, float* ws, void* stream);
 /* nn.LayerNorm(C, eps=1e-6) (trainer/model/modules/transformer.py:82, position_ffn.py:21) */
 int pk_layernorm_fwd(const void* x, void* y, int dtype, long long rows, int C, const float* w, const float* b, float eps,
                      float* mean, float* rstd, void* stream);
@@ -199,6 +202,26 @@ int pk_frontend_fwd(const short* pcm, long long ld_pcm, const int* n_samples, co
 int pk_fbank(const float* wave, long long ld_wave, const int* n_frames, int B, int t_max, int n_mel, const float* window,
              const float* twiddle, const float* mel_w, const int* mel_lo, const int* mel_hi, float preemph, float* feats,
              void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched beam search (pika_b200/csrc/beam.cu): one launch per step for the whole batch.
+ * Replaces decoder/beam_transducer.py:82-187 (BeamMergeTransducer.advance) and the gather / masked LSTM
+ * update / state reordering of decoder/transducer_decoder.py:127-150,173-178,188-202.  Rows are
+ * utterance-major (row = b*K + k); blank = blk, EOS = -1.
+ */
+int pk_beam_prepare(const int* tok, int* t_idx, const void* enc, int dtype, int Tenc, int H, void* enc_hid,
+                    const float* embed, int E, void* x_emb, int ld_x, int K, int blk, int rows, void* stream);
+int pk_beam_lstm_cell(const float* gates, const int* tok, int blk, void* h, int dtype, float* c, int rows, int H, void* stream);
+int pk_beam_gate(const float* a, void* h, int dtype, int rows, int H, void* stream);
+/* one BeamMergeTransducer.advance for every utterance: word_probs [B*K, V] f32 log-probs, t_idx [B*K],
+ * histories next_ys [S+1,B,K], prev_ks [S,B,K]; partial hypotheses hyp_tok [2,B,K,L] / hyp_len [2,B,K];
+ * finished lists fin_* [B,cap]; *not_done_total is decremented when an utterance becomes done. */
+int pk_beam_advance(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+                    int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
+                    int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
+                    int step, int blk, int n_best, int beam_prune, void* stream);
+int pk_beam_reorder(const int* prev_k, const void* h_in, const float* c_in, const int* t_in, void* h_out, float* c_out,
+                    int* t_out, int dtype, int K, int H, int layers, int rows, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,7 @@ class GemmDesc(ctypes.Structure):
         ("aux_stride", ctypes.c_int64 * 3),
         ("aux_scale", ctypes.c_float),
         ("block_n", ctypes.c_int),
+        ("k_splits", ctypes.c_int),
     ]
 
 

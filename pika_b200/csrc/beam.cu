@@ -1,0 +1,306 @@
+// Device-resident batched beam search for the transducer (decode + MBR N-best).
+//
+// Replaces the per-utterance Python bookkeeping of decoder/beam_transducer.py:82-187
+// (BeamMergeTransducer.advance: score add, EOS / duplicate-hypothesis kill, top-k over beam*V,
+// finish rule, partial-hypothesis update) and the gather / state-reorder steps of
+// decoder/transducer_decoder.py:127-150,188-202, for ALL utterances of the batch in one launch
+// per step, with no host round trip except a single "all done" flag.
+//
+// Row layout: row = b * K + k (utterance-major).  blank = blk, EOS = -1 as in the reference.
+#include "../../include/pika_b200.h"
+#include "common.cuh"
+
+namespace pk {
+void count_launch();
+
+constexpr float kKill = -1e20f;
+
+// ------------------------------------------------------------------------------------ step prologue
+// t_idx += (tok == blk); enc_hid[row] = enc[b, t_idx[row]]; x_emb[row] = embed[tok] (zeros unless tok > blk)
+template <typename T>
+__global__ void beam_prepare_kernel(const int* __restrict__ tok, int* __restrict__ t_idx, const T* __restrict__ enc, int Tenc, int H,
+                                    T* __restrict__ enc_hid, const float* __restrict__ embed, int E, T* __restrict__ x_emb, int ld_x,
+                                    int K, int blk, int rows) {
+    const int row = blockIdx.x;
+    if (row >= rows) return;
+    const int b = row / K;
+    const int tk = tok[row];
+    __shared__ int s_t;
+    if (threadIdx.x == 0) {
+        int t = t_idx[row] + (tk == blk ? 1 : 0);
+        t_idx[row] = t;
+        s_t = min(max(t, 0), Tenc - 1);
+    }
+    __syncthreads();
+    const T* src = enc + ((long long)b * Tenc + s_t) * H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) enc_hid[(long long)row * H + c] = src[c];
+    for (int c = threadIdx.x; c < ld_x; c += blockDim.x)
+        x_emb[(long long)row * ld_x + c] = from_f32<T>((tk > blk && c < E) ? embed[(long long)tk * E + c] : 0.f);
+}
+
+// LSTM cell on rows whose current token is a real label (tok > blk); other rows keep (h, c).
+template <typename T>
+__global__ void beam_lstm_cell_kernel(const float* __restrict__ gates, const int* __restrict__ tok, int blk, T* __restrict__ h,
+                                      float* __restrict__ c, int rows, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * H) return;
+    const int r = i / H, j = i - r * H;
+    if (!(tok[r] > blk)) return;
+    const float* g = gates + (long long)r * 4 * H;
+    const float gi = 1.f / (1.f + expf(-g[j])), gf = 1.f / (1.f + expf(-g[H + j]));
+    const float gg = tanhf(g[2 * H + j]), go = 1.f / (1.f + expf(-g[3 * H + j]));
+    const float cn = gf * c[i] + gi * gg;
+    c[i] = cn;
+    h[i] = from_f32<T>(go * tanhf(cn));
+}
+
+// h = tanh(a[:, :H]) * sigmoid(a[:, H:])   (gated joint on [rows, 2H] pre-activations)
+template <typename T>
+__global__ void beam_gate_kernel(const float* __restrict__ a, T* __restrict__ h, int rows, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * H) return;
+    const int r = i / H, j = i - r * H;
+    const float x = a[(long long)r * 2 * H + j], g = a[(long long)r * 2 * H + H + j];
+    h[i] = from_f32<T>(tanhf(x) * (1.f / (1.f + expf(-g))));
+}
+
+// ------------------------------------------------------------------------------------ beam advance
+struct BeamState {
+    float* scores;      // [B,K]
+    int* next_ys;       // [S+1, B, K]  (entry 0 = initial blk)
+    int* prev_ks;       // [S, B, K]
+    int* hyp_tok;       // [2, B, K, L] partial (non-blank) hypotheses, ping-pong by step parity
+    int* hyp_len;       // [2, B, K]
+    float* fin_score;   // [B, cap]
+    int* fin_step;      // [B, cap]
+    int* fin_k;         // [B, cap]
+    int* fin_count;     // [B]
+    int* eos_top;       // [B]
+    int* done;          // [B]
+    int* not_done_total;  // [1] number of utterances not yet done (written every step)
+};
+
+template <int K>
+PK_DEVICE void topk_insert(float (&v)[K], int (&ix)[K], float x, int id) {
+    // keeps v descending; ties keep the earlier (smaller-index) element first
+    if (!(x > v[K - 1])) return;
+    v[K - 1] = x; ix[K - 1] = id;
+#pragma unroll
+    for (int j = K - 1; j > 0; --j) {
+        if (v[j] > v[j - 1]) {
+            const float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
+            const int ti = ix[j]; ix[j] = ix[j - 1]; ix[j - 1] = ti;
+        }
+    }
+}
+
+constexpr int ADV_THREADS = 256;
+
+template <int K>
+__global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* __restrict__ word_probs, const int* __restrict__ t_idx,
+                                                                   const int* __restrict__ num_frames, const int* __restrict__ max_len,
+                                                                   BeamState st, int B, int V, int L, int cap, int step, int blk,
+                                                                   int n_best, int beam_prune) {
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ float s_rowscore[K];
+    __shared__ int s_kill[K];
+    __shared__ float s_cv[ADV_THREADS * K];
+    __shared__ int s_ci[ADV_THREADS * K];
+    __shared__ float s_best[K];
+    __shared__ int s_besti[K];
+    __shared__ float s_redv[ADV_THREADS / 32];
+    __shared__ int s_redi[ADV_THREADS / 32];
+    __shared__ int s_redp[ADV_THREADS / 32];
+
+    const int par_old = step & 1, par_new = par_old ^ 1;
+    const int* cur_tok = st.next_ys + ((long long)step * B + b) * K;
+    const int* old_hyp = st.hyp_tok + (((long long)par_old * B + b) * K) * L;
+    const int* old_len = st.hyp_len + ((long long)par_old * B + b) * K;
+    int* new_hyp = st.hyp_tok + (((long long)par_new * B + b) * K) * L;
+    int* new_len = st.hyp_len + ((long long)par_new * B + b) * K;
+
+    // ---- 1. which beam rows may have children
+    if (tid < K) {
+        s_rowscore[tid] = st.scores[b * K + tid];
+        int kill = 0;
+        if (step > 0) {
+            if (cur_tok[tid] == -1) kill = 1;                                  // finished beams have no children
+            else if (beam_prune && old_len[tid] > 0) {                          // duplicate partial hypothesis: first row wins
+                for (int j = 0; j < tid && !kill; ++j) {
+                    if (cur_tok[j] == -1 || old_len[j] != old_len[tid]) continue;
+                    bool same = true;
+                    for (int q = 0; q < old_len[tid]; ++q)
+                        if (old_hyp[(long long)j * L + q] != old_hyp[(long long)tid * L + q]) { same = false; break; }
+                    if (same) kill = 1;
+                }
+            }
+        } else if (tid > 0) {
+            kill = 2;                                                           // first step: only row 0 is expanded
+        }
+        s_kill[tid] = kill;
+    }
+    __syncthreads();
+
+    // ---- 2. per-thread top-K over the K*V candidates (flat index = k*V + v)
+    float lv[K];
+    int li[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { lv[j] = -INFINITY; li[j] = 0x7fffffff; }
+    const float* wp = word_probs + (long long)b * K * V;
+    const int total = K * V;
+    for (int id = tid; id < total; id += ADV_THREADS) {
+        const int k = id / V;
+        float x;
+        if (s_kill[k] == 2) continue;
+        if (s_kill[k] == 1) x = kKill;
+        else x = (step > 0) ? (wp[id] + s_rowscore[k]) : wp[id];
+        topk_insert<K>(lv, li, x, id);
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) { s_cv[tid * K + j] = lv[j]; s_ci[tid * K + j] = li[j]; }
+    __syncthreads();
+    // ---- 3. K rounds of block-wide arg-max over the ADV_THREADS*K candidates (value desc, index asc)
+    for (int round = 0; round < K; ++round) {
+        float bv = -INFINITY; int bi = 0x7fffffff, bp = -1;
+        for (int p = tid; p < ADV_THREADS * K; p += ADV_THREADS) {
+            const float v = s_cv[p]; const int ii = s_ci[p];
+            if (ii != 0x7fffffff && (v > bv || (v == bv && ii < bi) || bp < 0)) { bv = v; bi = ii; bp = p; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (op >= 0 && (bp < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bp = op; }
+        }
+        if ((tid & 31) == 0) { s_redv[tid >> 5] = bv; s_redi[tid >> 5] = bi; s_redp[tid >> 5] = bp; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < ADV_THREADS / 32; ++w) {
+                if (s_redp[w] >= 0 && (bp < 0 || s_redv[w] > bv || (s_redv[w] == bv && s_redi[w] < bi))) {
+                    bv = s_redv[w]; bi = s_redi[w]; bp = s_redp[w];
+                }
+            }
+            s_best[round] = bv; s_besti[round] = bi;
+            if (bp >= 0) s_ci[bp] = 0x7fffffff;                                 // consume
+        }
+        __syncthreads();
+    }
+
+    // ---- 4. new beam: back-pointers, tokens, scores, finish rule, partial hypotheses
+    int* out_tok = st.next_ys + ((long long)(step + 1) * B + b) * K;
+    int* out_prev = st.prev_ks + ((long long)step * B + b) * K;
+    const int nf = num_frames[b];
+    const int len_after = step + 2;                                             // len(self.next_ys) after the append
+    __shared__ int s_fin[K];
+    if (tid < K) {
+        const int id = s_besti[tid];
+        const int pk = id / V, y = id - pk * V;
+        const float sc = s_best[tid];
+        out_prev[tid] = pk;
+        st.scores[b * K + tid] = sc;
+        const bool fin = (y == blk && t_idx[b * K + pk] == nf - 1) || (len_after > max_len[b]);
+        out_tok[tid] = fin ? -1 : y;
+        s_fin[tid] = fin ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int cnt = st.fin_count[b];
+        for (int i = 0; i < K; ++i) {
+            if (s_fin[i] && cnt < cap) {
+                st.fin_score[(long long)b * cap + cnt] = s_best[i];
+                st.fin_step[(long long)b * cap + cnt] = step + 1;
+                st.fin_k[(long long)b * cap + cnt] = i;
+                ++cnt;
+            }
+        }
+        st.fin_count[b] = cnt;
+        int et = st.eos_top[b];
+        if (s_fin[0]) et = 1;
+        st.eos_top[b] = et;
+        const int dn = (et && cnt >= n_best) ? 1 : 0;
+        if (dn && !st.done[b]) { st.done[b] = 1; atomicSub(st.not_done_total, 1); }
+    }
+    // partial hypotheses: new[k] = finished ? old[k] : old[prev_k] (+ y if y != blk)
+    for (int k = 0; k < K; ++k) {
+        const int pk = s_besti[k] / V, y = s_besti[k] - (s_besti[k] / V) * V;
+        const int src = s_fin[k] ? k : pk;
+        const int n = old_len[src];
+        for (int q = tid; q < n; q += ADV_THREADS) new_hyp[(long long)k * L + q] = old_hyp[(long long)src * L + q];
+        if (tid == 0) {
+            int nn = n;
+            if (!s_fin[k] && y != blk && nn < L) { new_hyp[(long long)k * L + nn] = y; ++nn; }
+            new_len[k] = nn;
+        }
+    }
+}
+
+// dec_states / t_idx reordering by the new back-pointers (TransducerDecoder._beam_update)
+template <typename T>
+__global__ void beam_reorder_kernel(const int* __restrict__ prev_k, const T* __restrict__ h_in, const float* __restrict__ c_in,
+                                    const int* __restrict__ t_in, T* __restrict__ h_out, float* __restrict__ c_out, int* __restrict__ t_out,
+                                    int K, int H, int layers, int rows) {
+    const int row = blockIdx.x;
+    const int b = row / K;
+    const int src = b * K + prev_k[row];
+    for (int l = 0; l < layers; ++l) {
+        const long long o = ((long long)l * rows + row) * H, s = ((long long)l * rows + src) * H;
+        for (int c = threadIdx.x; c < H; c += blockDim.x) { h_out[o + c] = h_in[s + c]; c_out[o + c] = c_in[s + c]; }
+    }
+    if (threadIdx.x == 0) t_out[row] = t_in[src];
+}
+}  // namespace pk
+
+using namespace pk;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int pk_beam_prepare(const int* tok, int* t_idx, const void* enc, int dtype, int Tenc, int H, void* enc_hid,
+                               const float* embed, int E, void* x_emb, int ld_x, int K, int blk, int rows, void* stream) {
+    if (dtype == PK_BF16)
+        beam_prepare_kernel<__nv_bfloat16><<<rows, 128, 0, ST(stream)>>>(tok, t_idx, (const __nv_bfloat16*)enc, Tenc, H, (__nv_bfloat16*)enc_hid,
+                                                                        embed, E, (__nv_bfloat16*)x_emb, ld_x, K, blk, rows);
+    else
+        beam_prepare_kernel<float><<<rows, 128, 0, ST(stream)>>>(tok, t_idx, (const float*)enc, Tenc, H, (float*)enc_hid, embed, E,
+                                                                (float*)x_emb, ld_x, K, blk, rows);
+    PK_CHECK_LAUNCH(); count_launch();
+    return 0;
+}
+extern "C" int pk_beam_lstm_cell(const float* gates, const int* tok, int blk, void* h, int dtype, float* c, int rows, int H, void* stream) {
+    const int n = rows * H;
+    if (dtype == PK_BF16) beam_lstm_cell_kernel<__nv_bfloat16><<<(n + 255) / 256, 256, 0, ST(stream)>>>(gates, tok, blk, (__nv_bfloat16*)h, c, rows, H);
+    else beam_lstm_cell_kernel<float><<<(n + 255) / 256, 256, 0, ST(stream)>>>(gates, tok, blk, (float*)h, c, rows, H);
+    PK_CHECK_LAUNCH(); count_launch();
+    return 0;
+}
+extern "C" int pk_beam_gate(const float* a, void* h, int dtype, int rows, int H, void* stream) {
+    const int n = rows * H;
+    if (dtype == PK_BF16) beam_gate_kernel<__nv_bfloat16><<<(n + 255) / 256, 256, 0, ST(stream)>>>(a, (__nv_bfloat16*)h, rows, H);
+    else beam_gate_kernel<float><<<(n + 255) / 256, 256, 0, ST(stream)>>>(a, (float*)h, rows, H);
+    PK_CHECK_LAUNCH(); count_launch();
+    return 0;
+}
+extern "C" int pk_beam_advance(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+                               int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
+                               int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
+                               int step, int blk, int n_best, int beam_prune, void* stream) {
+    BeamState st{scores, next_ys, prev_ks, hyp_tok, hyp_len, fin_score, fin_step, fin_k, fin_count, eos_top, done, not_done_total};
+    PK_CHECK_ARG(V >= K, "vocabulary smaller than the beam");
+    switch (K) {
+#define CASE(KK) case KK: beam_advance_kernel<KK><<<B, ADV_THREADS, 0, ST(stream)>>>(word_probs, t_idx, num_frames, max_len, st, B, V, L, cap, step, blk, n_best, beam_prune); break;
+        CASE(1) CASE(2) CASE(4) CASE(8) CASE(16)
+#undef CASE
+        default: PK_CHECK_ARG(false, "beam size must be 1, 2, 4, 8 or 16");
+    }
+    PK_CHECK_LAUNCH(); count_launch();
+    return 0;
+}
+extern "C" int pk_beam_reorder(const int* prev_k, const void* h_in, const float* c_in, const int* t_in, void* h_out, float* c_out,
+                               int* t_out, int dtype, int K, int H, int layers, int rows, void* stream) {
+    if (dtype == PK_BF16)
+        beam_reorder_kernel<__nv_bfloat16><<<rows, 128, 0, ST(stream)>>>(prev_k, (const __nv_bfloat16*)h_in, c_in, t_in, (__nv_bfloat16*)h_out, c_out, t_out, K, H, layers, rows);
+    else
+        beam_reorder_kernel<float><<<rows, 128, 0, ST(stream)>>>(prev_k, (const float*)h_in, c_in, t_in, (float*)h_out, c_out, t_out, K, H, layers, rows);
+    PK_CHECK_LAUNCH(); count_launch();
+    return 0;
+}

@@ -66,9 +66,9 @@ __global__ void cast_split_kernel(const S* __restrict__ src, long long ld_src, _
 // sums[c] += sum_r f(x[r,c]); sums2[c] += sum_r x[r,c]*g[r,c]  (g = x for BN stats, x_hat for BN/LN bwd)
 // Block: 128 threads x 8 channels = 1024 channels per pass; rows split across blockIdx.y.
 template <typename T, int MODE>   // MODE 0: (sum x, sum x^2); 1: (sum dy, sum dy*xhat) with xhat=(x-mean)*rstd
-__global__ void __launch_bounds__(128) colstats_kernel(const T* __restrict__ x, const T* __restrict__ aux, long long rows, int C,
+__global__ void __launch_bounds__(128, 4) colstats_kernel(const T* __restrict__ x, const T* __restrict__ aux, long long rows, int C,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                       float* __restrict__ s1, float* __restrict__ s2) {
+                                                       float* __restrict__ s1) {
     const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
     if (c0 >= C) return;
     const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
@@ -80,23 +80,60 @@ __global__ void __launch_bounds__(128) colstats_kernel(const T* __restrict__ x, 
 #pragma unroll
         for (int e = 0; e < 8; ++e) { mu[e] = mean[c0 + e]; rs[e] = rstd[c0 + e]; }
     }
-    for (long long r = r0; r < r1; ++r) {
-        float f[8];
-        V8<T>::load(x + r * C + c0, f);
-        if (MODE == 0) {
+    constexpr int UR = 8;                       // independent 16-byte loads in flight per thread
+    long long r = r0;
+    for (; r + UR <= r1; r += UR) {
+        float f[UR][8], g[UR][8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * f[e]; }
-        } else {
-            float g[8];
-            V8<T>::load(aux + r * C + c0, g);          // aux = BN input x; f = dy
+        for (int k = 0; k < UR; ++k) {
+            V8<T>::load(x + (r + k) * C + c0, f[k]);
+            if (MODE == 1) V8<T>::load(aux + (r + k) * C + c0, g[k]);        // aux = BN input x; f = dy
+        }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { a[e] += f[e]; b[e] += f[e] * (g[e] - mu[e]) * rs[e]; }
+        for (int k = 0; k < UR; ++k) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                a[e] += f[k][e];
+                b[e] += (MODE == 0) ? f[k][e] * f[k][e] : f[k][e] * (g[k][e] - mu[e]) * rs[e];
+            }
         }
     }
+    for (; r < r1; ++r) {
+        float f[8], g[8];
+        V8<T>::load(x + r * C + c0, f);
+        if (MODE == 1) V8<T>::load(aux + r * C + c0, g);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        atomicAdd(&s1[c0 + e], a[e]);
-        if (s2) atomicAdd(&s2[c0 + e], b[e]);
+        for (int e = 0; e < 8; ++e) {
+            a[e] += f[e];
+            b[e] += (MODE == 0) ? f[e] * f[e] : f[e] * (g[e] - mu[e]) * rs[e];
+        }
+    }
+    // partial sums of this row-slice: part[(blockIdx.y * 2 + {0,1}) * C + c]
+    float* p1 = s1 + (long long)(blockIdx.y * 2) * C + c0;
+    float* p2 = p1 + C;
+    *reinterpret_cast<float4*>(p1) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(p1 + 4) = make_float4(a[4], a[5], a[6], a[7]);
+    *reinterpret_cast<float4*>(p2) = make_float4(b[0], b[1], b[2], b[3]);
+    *reinterpret_cast<float4*>(p2 + 4) = make_float4(b[4], b[5], b[6], b[7]);
+}
+// out1[c] = sum_y part[y][0][c], out2[c] = sum_y part[y][1][c]   (fixed order: deterministic)
+// block = 32 columns x 8 y-groups
+__global__ void __launch_bounds__(256) colstats_reduce_kernel(const float* __restrict__ part, int gy, int C, float* __restrict__ out1,
+                                                              float* __restrict__ out2) {
+    __shared__ float sa[8][33], sb[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float a = 0.f, b = 0.f;
+    if (c < C) {
+        for (int y = ty; y < gy; y += 8) { a += part[(long long)(y * 2) * C + c]; b += part[(long long)(y * 2 + 1) * C + c]; }
+    }
+    sa[ty][tx] = a; sb[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { a += sa[k][tx]; b += sb[k][tx]; }
+        out1[c] = a;
+        if (out2) out2[c] = b;
     }
 }
 
@@ -285,6 +322,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 
 // =============================================================================== attention softmax
 // S f32 [rows, ld_s] (first n valid) -> P (T) [rows, ld_p] and Pd = dropout(P); pad columns [n, ld_p) zeroed.
+// One warp per row; the row lives in registers (lane l owns columns [l*8 + k*256, +8), k < 4, n <= 1024) and every
+// access is a 16/32-byte vector, so S is read exactly once.  ld_s, ld_p multiples of 8.
+constexpr int SM_CH = 4;
+PK_DEVICE void ld8f(const float* p, float (&f)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, long long ld_s, T* __restrict__ P,
                                                           T* __restrict__ Pd, long long ld_p, long long rows, int n,
@@ -294,21 +338,38 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long r = warp; r < rows; r += nw) {
         const float* sr = S + r * ld_s;
+        float v[SM_CH][8];
         float m = -INFINITY;
-        for (int c = lane; c < n; c += 32) m = fmaxf(m, sr[c]);
+#pragma unroll
+        for (int k = 0; k < SM_CH; ++k) {
+            const int c0 = lane * 8 + k * 256;
+            if (c0 < (int)ld_p) ld8f(sr + c0, v[k]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (c0 + e >= n) v[k][e] = -INFINITY;
+                m = fmaxf(m, v[k][e]);
+            }
+        }
         m = warp_max(m);
         float s = 0.f;
-        for (int c = lane; c < n; c += 32) s += __expf(sr[c] - m);
+#pragma unroll
+        for (int k = 0; k < SM_CH; ++k)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[k][e] = __expf(v[k][e] - m); s += v[k][e]; }
         const float inv = 1.f / warp_sum(s);
-        for (int c = lane; c < (int)ld_p; c += 32) {
-            float p = 0.f;
-            if (c < n) p = __expf(sr[c] - m) * inv;
-            const T pt = from_f32<T>(p);
-            P[r * ld_p + c] = pt;
-            if (Pd != P) {
-                float pd = to_f32<T>(pt);
-                if (drop_thresh) pd = drop_keep((uint64_t)r * (uint64_t)n + c, seed, drop_thresh) ? pd * drop_scale : 0.f;
-                Pd[r * ld_p + c] = from_f32<T>(pd);
+#pragma unroll
+        for (int k = 0; k < SM_CH; ++k) {
+            const int c0 = lane * 8 + k * 256;
+            if (c0 < (int)ld_p) {
+                float o[8], od[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o[e] = to_f32<T>(from_f32<T>(v[k][e] * inv));        // dropout acts on the rounded probability
+                    od[e] = o[e];
+                    if (drop_thresh) od[e] = drop_keep((uint64_t)r * (uint64_t)n + c0 + e, seed, drop_thresh) ? o[e] * drop_scale : 0.f;
+                }
+                V8<T>::store(P + r * ld_p + c0, o);
+                if (Pd != P) V8<T>::store(Pd + r * ld_p + c0, od);
             }
         }
     }
@@ -322,21 +383,32 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long r = warp; r < rows; r += nw) {
+        float d[SM_CH][8], pv[SM_CH][8];
         float dot = 0.f;
-        for (int c = lane; c < n; c += 32) {
-            float d = dPd[r * ld_d + c];
-            if (drop_thresh) d = drop_keep((uint64_t)r * (uint64_t)n + c, seed, drop_thresh) ? d * drop_scale : 0.f;
-            dot += d * to_f32<T>(P[r * ld_p + c]);
+#pragma unroll
+        for (int k = 0; k < SM_CH; ++k) {
+            const int c0 = lane * 8 + k * 256;
+            if (c0 < (int)ld_p) {
+                ld8f(dPd + r * ld_d + c0, d[k]);
+                V8<T>::load(P + r * ld_p + c0, pv[k]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (c0 + e >= n) { d[k][e] = 0.f; pv[k][e] = 0.f; }
+                    else if (drop_thresh) d[k][e] = drop_keep((uint64_t)r * (uint64_t)n + c0 + e, seed, drop_thresh) ? d[k][e] * drop_scale : 0.f;
+                    dot += d[k][e] * pv[k][e];
+                }
+            }
         }
         dot = warp_sum(dot);
-        for (int c = lane; c < (int)ld_p; c += 32) {
-            float o = 0.f;
-            if (c < n) {
-                float d = dPd[r * ld_d + c];
-                if (drop_thresh) d = drop_keep((uint64_t)r * (uint64_t)n + c, seed, drop_thresh) ? d * drop_scale : 0.f;
-                o = to_f32<T>(P[r * ld_p + c]) * (d - dot);
+#pragma unroll
+        for (int k = 0; k < SM_CH; ++k) {
+            const int c0 = lane * 8 + k * 256;
+            if (c0 < (int)ld_p) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = pv[k][e] * (d[k][e] - dot);
+                V8<T>::store(dS + r * ld_p + c0, o);
             }
-            dS[r * ld_p + c] = from_f32<T>(o);
         }
     }
 }
@@ -385,6 +457,17 @@ __global__ void __launch_bounds__(256) log_softmax_kernel(const T* __restrict__ 
 // h[b,t,u,c] = tanh(e1[b,t,c] + p1[b,u,c]) * sigmoid(eg[b,t,c] + pg[b,u,c])
 // ex = [B*T, 2H] (cols [0,H) = fc1 part, [H,2H) = gate part), py = [B*U1, 2H]; biases already folded into ex.
 PK_DEVICE float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// activation pair of the gated joint: precise libm in the fp32-class mode, MUFU.TANH in production (bf16)
+template <typename T> PK_DEVICE float jt_tanh(float x);
+template <> PK_DEVICE float jt_tanh<float>(float x) { return tanhf(x); }
+template <> PK_DEVICE float jt_tanh<__nv_bfloat16>(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <typename T> PK_DEVICE float jt_sigmoid(float x);
+template <> PK_DEVICE float jt_sigmoid<float>(float x) { return 1.f / (1.f + expf(-x)); }
+template <> PK_DEVICE float jt_sigmoid<__nv_bfloat16>(float x) { return fmaf(jt_tanh<__nv_bfloat16>(0.5f * x), 0.5f, 0.5f); }
 
 template <typename T>
 __global__ void __launch_bounds__(128) joint_gate_fwd_kernel(const T* __restrict__ ex, const T* __restrict__ py, T* __restrict__ h,
@@ -402,7 +485,7 @@ __global__ void __launch_bounds__(128) joint_gate_fwd_kernel(const T* __restrict
             V8<T>::load(pr + c0, p1);
             V8<T>::load(pr + H + c0, pg);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = tanhf(e1[e] + p1[e]) * sigmoidf_(eg[e] + pg[e]);
+            for (int e = 0; e < 8; ++e) o[e] = jt_tanh<T>(e1[e] + p1[e]) * jt_sigmoid<T>(eg[e] + pg[e]);
             V8<T>::store(h + ((long long)bt * U1 + u) * H + c0, o);
         }
     }
@@ -426,7 +509,7 @@ __global__ void __launch_bounds__(128) joint_gate_bwd_ex_kernel(const T* __restr
             V8<T>::load(dh + ((long long)bt * U1 + u) * H + c0, d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float a = tanhf(e1[e] + p1[e]), g = sigmoidf_(eg[e] + pg[e]);
+                const float a = jt_tanh<T>(e1[e] + p1[e]), g = jt_sigmoid<T>(eg[e] + pg[e]);
                 a1[e] += d[e] * g * (1.f - a * a);
                 ag[e] += d[e] * a * g * (1.f - g);
             }
@@ -454,7 +537,7 @@ __global__ void __launch_bounds__(128) joint_gate_bwd_py_kernel(const T* __restr
             V8<T>::load(dh + (bt * U1 + u) * H + c0, d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float a = tanhf(e1[e] + p1[e]), g = sigmoidf_(eg[e] + pg[e]);
+                const float a = jt_tanh<T>(e1[e] + p1[e]), g = jt_sigmoid<T>(eg[e] + pg[e]);
                 a1[e] += d[e] * g * (1.f - a * a);
                 ag[e] += d[e] * a * g * (1.f - g);
             }
@@ -541,6 +624,23 @@ using namespace pk;
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 #define DONE() PK_CHECK_LAUNCH(); count_launch(); return 0
 
+// column statistics in two deterministic stages; ws must hold pk_colstats_ws_floats(C) floats
+static const int kColGy = 296;
+extern "C" long long pk_colstats_ws_floats(int C) { return (long long)kColGy * 2 * C; }
+template <typename T, int MODE>
+static int run_colstats(const T* x, const T* aux, long long rows, int C, const float* mean, const float* rstd, float* ws, float* out1,
+                        float* out2, cudaStream_t st) {
+    int gy = (int)((rows + 63) / 64);
+    if (gy > kColGy) gy = kColGy;
+    if (gy < 1) gy = 1;
+    dim3 g((C / 8 + 127) / 128, gy);
+    colstats_kernel<T, MODE><<<g, 128, 0, st>>>(x, aux, rows, C, mean, rstd, ws);
+    PK_CHECK_LAUNCH(); count_launch();
+    colstats_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, gy, C, out1, out2);
+    PK_CHECK_LAUNCH(); count_launch();
+    return 0;
+}
+
 static uint32_t drop_thresh_of(float p) {
     if (p <= 0.f) return 0u;
     double t = (double)p * 4294967296.0;
@@ -561,18 +661,16 @@ extern "C" int pk_cast_split(const void* src, int src_dtype, long long ld_src, v
     DONE();
 }
 
-/* BatchNorm1d over rows of x [rows, C].  stats_ws: 4*C floats (zeroed by the caller for train mode). */
+/* BatchNorm1d over rows of x [rows, C].  stats_ws: pk_colstats_ws_floats(C) + 2*C floats of scratch. */
 extern "C" int pk_bn_fwd(const void* x, void* y, int dtype, long long rows, int C, const float* w, const float* b, float eps,
                          int train, float momentum, float* run_mean, float* run_var, float* mean, float* rstd, float* stats_ws,
                          void* stream) {
     PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
     cudaStream_t st = STREAM(stream);
     if (train) {
-        PK_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * C, st));
-        dim3 g((C / 8 + 127) / 128, (unsigned)grid_for(rows, 64, 4));
-        PK_DISPATCH_T(dtype, (colstats_kernel<T, 0><<<g, 128, 0, st>>>((const T*)x, nullptr, rows, C, nullptr, nullptr, stats_ws, stats_ws + C)));
-        PK_CHECK_LAUNCH(); count_launch();
-        bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(stats_ws, stats_ws + C, rows, C, eps, momentum, mean, rstd, run_mean, run_var);
+        float* sums = stats_ws + pk_colstats_ws_floats(C);
+        PK_DISPATCH_T(dtype, { int rc = run_colstats<T, 0>((const T*)x, nullptr, rows, C, nullptr, nullptr, stats_ws, sums, sums + C, st); if (rc) return rc; });
+        bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, sums + C, rows, C, eps, momentum, mean, rstd, run_mean, run_var);
     } else {
         bn_eval_stats_kernel<<<(C + 255) / 256, 256, 0, st>>>(run_mean, run_var, C, eps, mean, rstd);
     }
@@ -584,27 +682,22 @@ extern "C" int pk_bn_fwd(const void* x, void* y, int dtype, long long rows, int 
 
 /* dx (optionally ReLU-masked by x > 0), dw[C], db[C] (overwritten).  stats_ws: 2*C floats. */
 extern "C" int pk_bn_bwd(const void* dy, const void* x, void* dx, int dtype, long long rows, int C, const float* w,
-                         const float* mean, const float* rstd, int train, int relu_mask, float* dw, float* db, void* stream) {
+                         const float* mean, const float* rstd, int train, int relu_mask, float* dw, float* db, float* ws,
+                         void* stream) {
     PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
     cudaStream_t st = STREAM(stream);
-    PK_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
-    PK_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C, st));
-    dim3 g((C / 8 + 127) / 128, (unsigned)grid_for(rows, 64, 4));
-    PK_DISPATCH_T(dtype, (colstats_kernel<T, 1><<<g, 128, 0, st>>>((const T*)dy, (const T*)x, rows, C, mean, rstd, db, dw)));
-    PK_CHECK_LAUNCH(); count_launch();
+    PK_DISPATCH_T(dtype, { int rc = run_colstats<T, 1>((const T*)dy, (const T*)x, rows, C, mean, rstd, ws, db, dw, st); if (rc) return rc; });
     const int grid = grid_for(rows * C / 8, 256);
     PK_DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, (T*)dx, rows, C, mean, rstd, w,
                                                                        train ? db : nullptr, train ? dw : nullptr, relu_mask)));
     DONE();
 }
 
-extern "C" int pk_colsum(const void* x, int dtype, long long rows, int C, float* out, void* stream) {
+extern "C" int pk_colsum(const void* x, int dtype, long long rows, int C, float* out, float* ws, void* stream) {
     PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
     cudaStream_t st = STREAM(stream);
-    PK_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
-    dim3 g((C / 8 + 127) / 128, (unsigned)grid_for(rows, 64, 4));
-    PK_DISPATCH_T(dtype, (colstats_kernel<T, 0><<<g, 128, 0, st>>>((const T*)x, nullptr, rows, C, nullptr, nullptr, out, nullptr)));
-    DONE();
+    PK_DISPATCH_T(dtype, { int rc = run_colstats<T, 0>((const T*)x, nullptr, rows, C, nullptr, nullptr, ws, out, nullptr, st); if (rc) return rc; });
+    return 0;
 }
 
 extern "C" int pk_layernorm_fwd(const void* x, void* y, int dtype, long long rows, int C, const float* w, const float* b, float eps,
@@ -628,7 +721,7 @@ extern "C" int pk_layernorm_bwd(const void* dy, const void* x, void* dx, int dty
 
 extern "C" int pk_softmax_fwd(const float* S, long long ld_s, void* P, void* Pd, int dtype, long long ld_p, long long rows, int n,
                               float drop_p, uint32_t seed, void* stream) {
-    PK_CHECK_ARG(rows > 0 && n > 0 && ld_p >= n && ld_s >= n, "bad shape");
+    PK_CHECK_ARG(rows > 0 && n > 0 && ld_p >= n && ld_s >= ld_p && ld_p <= 1024 && ld_p % 8 == 0 && ld_s % 8 == 0, "softmax rows: ld % 8 == 0, <= 1024 wide");
     const int grid = grid_for(rows, 8);
     const uint32_t th = drop_thresh_of(drop_p);
     const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;

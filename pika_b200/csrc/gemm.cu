@@ -33,6 +33,7 @@ struct GemmParams {
     int a_off[PK_GEMM_MAX_PAIRS];
     int b_off[PK_GEMM_MAX_PAIRS];
     int n_pairs, kz_count, num_k_blocks;
+    int k_splits, iters_per_split;      // split-K over the flattened (pair, kz, k-block) iteration space
     int M, N, tiles_m, tiles_n, zb0, zb1;
     int a_sel2, a_sel3, b_sel2, b_sel3;
     int c_is_f32, c_accumulate;
@@ -104,48 +105,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const uint32_t tmem_base = *tmem_slot;
 
     const int tiles_per_z = p.tiles_m * p.tiles_n;
-    const int num_tiles = tiles_per_z * p.zb0 * p.zb1;
-    const int k_iters = p.n_pairs * p.kz_count * p.num_k_blocks;
+    const int num_tiles = tiles_per_z * p.zb0 * p.zb1 * p.k_splits;      // work units = tiles x K-splits
+    const int k_iters_total = p.n_pairs * p.kz_count * p.num_k_blocks;
+    const int kzb = p.kz_count * p.num_k_blocks;
 
     if (warp == 0) {
         // ===================================================== TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x) {
+                const int tile = unit / p.k_splits, split = unit - tile * p.k_splits;
                 const int z = tile / tiles_per_z;
                 const int r = tile - z * tiles_per_z;
                 const int mb = r / p.tiles_n, nb = r - mb * p.tiles_n;
                 const int zb1 = z / p.zb0, zb0 = z - zb1 * p.zb0;
                 const int m0 = mb * BM, n0 = nb * BN;
-                for (int pr = 0; pr < p.n_pairs; ++pr) {
-                    for (int kz = 0; kz < p.kz_count; ++kz) {
-                        const int a2 = pick_sel(p.a_sel2, zb0, zb1, kz), a3 = pick_sel(p.a_sel3, zb0, zb1, kz);
-                        const int b2 = pick_sel(p.b_sel2, zb0, zb1, kz), b3 = pick_sel(p.b_sel3, zb0, zb1, kz);
-                        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                            uint8_t* sb = sa + A_STAGE_BYTES;
-                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                            if (A_MN) {
+                const int i0 = split * p.iters_per_split, i1 = min(k_iters_total, i0 + p.iters_per_split);
+                for (int i = i0; i < i1; ++i) {
+                    const int pr = i / kzb;
+                    const int rem = i - pr * kzb;
+                    const int kz = rem / p.num_k_blocks, kb = rem - kz * p.num_k_blocks;
+                    const int a2 = pick_sel(p.a_sel2, zb0, zb1, kz), a3 = pick_sel(p.a_sel3, zb0, zb1, kz);
+                    const int b2 = pick_sel(p.b_sel2, zb0, zb1, kz), b3 = pick_sel(p.b_sel3, zb0, zb1, kz);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (A_MN) {
 #pragma unroll
-                                for (int i = 0; i < BM / 64; ++i)
-                                    tma_load_4d(sa + i * (64 * BK * 2), &p.a[pr], &full_bar[stage], m0 + i * 64,
-                                                kb * BK + p.a_off[pr], a2, a3);
-                            } else {
-                                tma_load_4d(sa, &p.a[pr], &full_bar[stage], kb * BK, m0 + p.a_off[pr], a2, a3);
-                            }
-                            if (B_MN) {
-#pragma unroll
-                                for (int i = 0; i < BN / 64; ++i)
-                                    tma_load_4d(sb + i * (64 * BK * 2), &p.b[pr], &full_bar[stage], n0 + i * 64,
-                                                kb * BK + p.b_off[pr], b2, b3);
-                            } else {
-                                tma_load_4d(sb, &p.b[pr], &full_bar[stage], kb * BK, n0 + p.b_off[pr], b2, b3);
-                            }
-                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-                        }
+                        for (int c = 0; c < BM / 64; ++c)
+                            tma_load_4d(sa + c * (64 * BK * 2), &p.a[pr], &full_bar[stage], m0 + c * 64, kb * BK + p.a_off[pr], a2, a3);
+                    } else {
+                        tma_load_4d(sa, &p.a[pr], &full_bar[stage], kb * BK, m0 + p.a_off[pr], a2, a3);
                     }
+                    if (B_MN) {
+#pragma unroll
+                        for (int c = 0; c < BN / 64; ++c)
+                            tma_load_4d(sb + c * (64 * BK * 2), &p.b[pr], &full_bar[stage], n0 + c * 64, kb * BK + p.b_off[pr], b2, b3);
+                    } else {
+                        tma_load_4d(sb, &p.b[pr], &full_bar[stage], kb * BK, n0 + p.b_off[pr], b2, b3);
+                    }
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -156,7 +157,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x, ++it) {
+                const int split = unit % p.k_splits;
+                const int k_iters = min(k_iters_total, (split + 1) * p.iters_per_split) - split * p.iters_per_split;
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -200,7 +203,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         }
         int it = 0;
         uint32_t chunk_ctr = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x, ++it) {
+            const int tile = unit / p.k_splits;
             const int z = tile / tiles_per_z;
             const int r = tile - z * tiles_per_z;
             const int mb = r / p.tiles_n, nb = r - mb * p.tiles_n;
@@ -450,7 +454,28 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
     gp.aux_sm = d->aux_stride[0]; gp.aux_s0 = d->aux_stride[1]; gp.aux_s1 = d->aux_stride[2];
     gp.aux_scale = d->aux_scale;
 
-    const long long num_tiles = (long long)gp.tiles_m * gp.tiles_n * gp.zb0 * gp.zb1;
+    const long long out_tiles = (long long)gp.tiles_m * gp.tiles_n * gp.zb0 * gp.zb1;
+    // split-K: under-filled grids with a long reduction (wgrad, the LSTM's recurrent dgrad) are cut along the
+    // flattened (pair, kz, k-block) axis; partial tiles are combined with TMA reduce-add into a zeroed f32 C.
+    const int k_iters_total = gp.n_pairs * gp.kz_count * gp.num_k_blocks;
+    int splits = 1;
+    const bool plain_epi = d->bias == nullptr && d->act == PK_ACT_NONE && d->drop_p == 0.f && gp.aux_mode == PK_AUX_NONE;
+    if (d->k_splits > 0) splits = d->k_splits;
+    else if (gp.c_is_f32 && plain_epi && gp.zb0 == 1 && gp.zb1 == 1 && out_tiles < 2 * num_sms() && k_iters_total >= 16) {
+        splits = (int)((2 * num_sms() + out_tiles / 2) / out_tiles);
+        if (splits > k_iters_total / 8) splits = k_iters_total / 8;
+        if (splits > 64) splits = 64;
+        if (splits < 1) splits = 1;
+    }
+    PK_CHECK_ARG(splits == 1 || (gp.c_is_f32 && plain_epi && gp.zb0 == 1 && gp.zb1 == 1), "split-K needs a plain f32 2-D C");
+    gp.iters_per_split = (k_iters_total + splits - 1) / splits;
+    gp.k_splits = (k_iters_total + gp.iters_per_split - 1) / gp.iters_per_split;
+    if (gp.k_splits > 1) {
+        if (!gp.c_accumulate)
+            PK_CHECK_CUDA(cudaMemset2DAsync(const_cast<void*>(d->c.ptr), (size_t)d->c.stride[0] * 4, 0, (size_t)N * 4, (size_t)M, stream));
+        gp.c_accumulate = 1;
+    }
+    const long long num_tiles = out_tiles * gp.k_splits;
     PK_CHECK_ARG(num_tiles < (1ll << 31), "too many tiles");
     int grid = num_sms();
     if (num_tiles < grid) grid = (int)num_tiles;

@@ -43,7 +43,7 @@ def _fill_view(v, t):
 
 def gemm(a, b, c, a_mn=False, b_mn=False, a_sel=(SEL_ZB0, SEL_ZB1), b_sel=(SEL_ZB0, SEL_ZB1), kz_count=1,
          a_row_off=None, b_row_off=None, alpha=1.0, bias=None, act=ACT_NONE, drop_p=0.0, drop_seed=0,
-         aux=None, aux_mode=AUX_NONE, aux_scale=1.0, accumulate=False, block_n=0):
+         aux=None, aux_mode=AUX_NONE, aux_scale=1.0, accumulate=False, block_n=0, k_splits=0):
     """C = epilogue(alpha * sum_p A_p @ B_p^T) on the tcgen05 tensor cores (include/pika_b200.h).
 
     a, b: a bf16 view or a list of views (pairs).  Views are torch tensors of <= 4 dims laid out
@@ -87,6 +87,7 @@ def gemm(a, b, c, a_mn=False, b_mn=False, a_sel=(SEL_ZB0, SEL_ZB1), b_sel=(SEL_Z
             d.aux_stride[i] = st[i + 1] if i + 1 < len(st) else 0
         d.aux_scale = aux_scale
     d.block_n = block_n
+    d.k_splits = k_splits
     check(lib.pk_gemm_bf16(ctypes.byref(d), _stream()), "pk_gemm_bf16")
     return c
 
@@ -127,8 +128,21 @@ def cast_split(src, hi, lo=None, cols_pad=None, scale=1.0):
                             _I(cols), _I(cols_pad), _F(scale), _stream()), "pk_cast_split")
 
 
-def bn_fwd(x, y, w, b, eps, train, momentum, run_mean, run_var, mean, rstd, ws):
+_col_ws = {}
+
+
+def col_ws(C, device):
+    """persistent scratch for the two-stage column reductions (per device, per C)"""
+    key = (C, str(device))
+    if key not in _col_ws:
+        lib.pk_colstats_ws_floats.restype = ctypes.c_longlong
+        _col_ws[key] = torch.empty(int(lib.pk_colstats_ws_floats(C)) + 2 * C, dtype=torch.float32, device=device)
+    return _col_ws[key]
+
+
+def bn_fwd(x, y, w, b, eps, train, momentum, run_mean, run_var, mean, rstd, ws=None):
     rows, C = x.shape
+    ws = col_ws(C, x.device)
     check(lib.pk_bn_fwd(_P(x), _P(y), _I(_dt(x)), _L(rows), _I(C), _P(w), _P(b), _F(eps), _I(int(train)), _F(momentum),
                         _P(run_mean), _P(run_var), _P(mean), _P(rstd), _P(ws), _stream()), "pk_bn_fwd")
 
@@ -136,13 +150,13 @@ def bn_fwd(x, y, w, b, eps, train, momentum, run_mean, run_var, mean, rstd, ws):
 def bn_bwd(dy, x, dx, w, mean, rstd, train, relu_mask, dw, db):
     rows, C = x.shape
     check(lib.pk_bn_bwd(_P(dy), _P(x), _P(dx), _I(_dt(x)), _L(rows), _I(C), _P(w), _P(mean), _P(rstd), _I(int(train)),
-                        _I(int(relu_mask)), _P(dw), _P(db), _stream()), "pk_bn_bwd")
+                        _I(int(relu_mask)), _P(dw), _P(db), _P(col_ws(C, x.device)), _stream()), "pk_bn_bwd")
 
 
 def colsum(x, out):
     rows, C = x.shape
     assert x.is_contiguous()
-    check(lib.pk_colsum(_P(x), _I(_dt(x)), _L(rows), _I(C), _P(out), _stream()), "pk_colsum")
+    check(lib.pk_colsum(_P(x), _I(_dt(x)), _L(rows), _I(C), _P(out), _P(col_ws(C, x.device)), _stream()), "pk_colsum")
 
 
 def layernorm_fwd(x, y, w, b, eps, mean, rstd):

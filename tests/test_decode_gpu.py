@@ -1,0 +1,76 @@
+"""Beam-search parity: hypothesis token-id sequences (full alignments incl. blanks) must be BIT-EXACT with the
+reference's TransducerDecoder.decode_batch output (tests/golden/decode_small.npz, produced by executing
+/root/reference on the CPU), scores within 1e-3 relative.  Runs in the fp32-class mode so that score margins
+are not eroded by bf16 rounding (the north star ties bit-exactness to reference-matching activations)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def build(V=40):
+    from fixture_utils import decode_fixture_reinit
+    from pika_b200.model.transducer import Net
+    torch.manual_seed(777)
+    args = types.SimpleNamespace(rnn_size=1024, local_rank=0, decoder_type="rnn", brnn=True, encoder_type="transformer",
+                                 embd_dim=100, padding_idx=V, dropout=0.2, dec_layers=2, enc_layers=9)
+    m = Net(args, 240, V)
+    decode_fixture_reinit(m)              # identical CPU RNG draws as in make_golden.py
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("name,beam,nbest,prune", [("b4n1", 4, 1, True), ("b4n4np", 4, 4, False), ("b8n2", 8, 2, True)])
+def test_decode_matches_reference_bit_exact(golden_dir, name, beam, nbest, prune):
+    from pika_b200 import engine
+    from pika_b200.decoder.beam_transducer import GlobalScorer
+    from pika_b200.decoder.transducer_decoder import TransducerDecoder
+    d = np.load(os.path.join(golden_dir, "decode_small.npz"))
+    engine.set_precision("fp32")
+    try:
+        m = build()
+        dargs = types.SimpleNamespace(las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None, nonblk_reward=0.0)
+        dec = TransducerDecoder(m, 3, beam, n_best=nbest, blk=0, global_scorer=GlobalScorer(), sm_scale=1.0, cuda=True,
+                                beam_prune=prune, args=dargs)
+        x = torch.from_numpy(d["x"]).cuda()
+        tl = torch.from_numpy(d["tlens"])
+        ret, enc = dec.decode_batch(x, tl, max_len=[int(t) + 100 for t in tl])
+        ref_enc = d["enc"]
+        got_enc = enc.cpu().numpy()[:, ::3, ::17]
+        assert np.linalg.norm(got_enc - ref_enc) / np.linalg.norm(ref_enc) < 1e-3
+        for b in range(3):
+            for n in range(nbest):
+                hyp = [int(t.item()) for t in ret["predictions"][b][n]]
+                ref = d["%s_pred_%d_%d" % (name, b, n)].tolist()
+                assert hyp == ref, (name, b, n, hyp[:40], ref[:40])
+                sc = float(ret["scores"][b][n])
+                assert abs(sc - float(d["%s_score_%d_%d" % (name, b, n)])) < 1e-3 * abs(sc) + 1e-3
+    finally:
+        engine.set_precision("bf16")
+
+
+def test_decode_bf16_runs_and_terminates():
+    """Production precision: shapes/termination/invariants (alignments end at the last frame or at max_len)."""
+    from pika_b200 import engine
+    from pika_b200.decoder.beam_transducer import GlobalScorer
+    from pika_b200.decoder.transducer_decoder import TransducerDecoder
+    engine.set_precision("bf16")
+    m = build()
+    dargs = types.SimpleNamespace(las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None, nonblk_reward=0.0)
+    dec = TransducerDecoder(m, 4, 4, n_best=2, blk=0, global_scorer=GlobalScorer(), cuda=True, beam_prune=True, args=dargs)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(4, 150, 240, generator=g).cuda()
+    tl = torch.tensor([27, 27, 20, 15])
+    ret, enc = dec.decode_batch(x, tl, max_len=[int(t) + 100 for t in tl])
+    assert tuple(enc.shape) == (4, 27, 1024)
+    for b in range(4):
+        assert len(ret["predictions"][b]) == 2
+        for hyp in ret["predictions"][b]:
+            toks = [int(t) for t in hyp]
+            blanks = sum(1 for t in toks if t == 0)
+            assert blanks == int(tl[b]) - 1 or len(toks) >= int(tl[b]) + 100 - 2     # consumed every frame, or hit max_len
+        s = [float(v) for v in ret["scores"][b]]
+        assert s[0] >= s[1]
