@@ -28,7 +28,10 @@ class BmufTrainer():
     ``backend`` -- "nccl" (default, as hard-coded in the reference) or "gloo" for CPU-side tests.
     """
 
-    def __init__(self, master_node, rank, world_size, model, block_momentum, block_lr, flat=None, backend="nccl"):
+    def __init__(self, master_node, rank, world_size, model, block_momentum, block_lr, flat=None, backend="nccl", ops=None):
+        # ``ops``: object with bmuf_delta / bmuf_update / absmax; defaults to the CUDA kernels.  The CPU-side
+        # gloo test injects the numpy oracle here to exercise the collective protocol without a GPU.
+        self.ops = ops if ops is not None else K
         self.master_node, self.rank, self.world_size = master_node, rank, world_size
         self.model, self.block_momentum, self.block_lr = model, block_momentum, block_lr
         if world_size > 1 and not dist.is_initialized():
@@ -46,14 +49,14 @@ class BmufTrainer():
 
     def update_and_sync(self):
         """one block sync: returns SUCCESS if numerics are healthy on every rank, STOP otherwise"""
-        K.bmuf_delta(self.param, self.flat.data, self.delta)
+        self.ops.bmuf_delta(self.param, self.flat.data, self.delta)
         if self.world_size > 1:
             dist.all_reduce(self.delta, op=dist.ReduceOp.SUM)
         self.nan_flag.zero_()
-        K.absmax(self.delta, self.health[:1], self.nan_flag)     # NaNs propagate through the sum: every rank sees them
+        self.ops.absmax(self.delta, self.health[:1], self.nan_flag)     # NaNs propagate through the sum: every rank sees them
         if int(self.nan_flag.item()) != 0:
             return STOP
-        K.bmuf_update(self.param, self.flat.data, self.delta_prev, self.delta, self.world_size, self.block_momentum, self.block_lr)
+        self.ops.bmuf_update(self.param, self.flat.data, self.delta_prev, self.delta, self.world_size, self.block_momentum, self.block_lr)
         engine.invalidate_weights()
         return SUCCESS
 

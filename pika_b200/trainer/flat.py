@@ -16,7 +16,7 @@ from .. import kernels as K
 class FlatParams:
     def __init__(self, model):
         params = [p for p in model.parameters()]
-        assert all(p.dtype == torch.float32 and p.is_cuda for p in params), "model must be fp32 on the GPU"
+        assert all(p.dtype == torch.float32 for p in params), "model parameters must be fp32"
         # 16-byte aligned slots so that every parameter can be a TMA source / destination
         offs, n = [], 0
         for p in params:

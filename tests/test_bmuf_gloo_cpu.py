@@ -1,0 +1,91 @@
+"""BMUF protocol across 2 ranks on CPU (gloo): the drop-in BmufTrainer's collective sequence
+(initial broadcast, all-reduce of the block delta, replicated block-momentum update, collective NaN stop,
+sum_reduce/broadcast helpers) against the oracle of trainer/bmuf.py:76-100.  The element-wise kernels are
+CUDA-only, so this host-logic test injects numpy implementations of the three ops (oracle/train.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class NumpyOps:
+    @staticmethod
+    def bmuf_delta(glob, local, delta):
+        delta.copy_(glob - local)
+
+    @staticmethod
+    def absmax(x, out, nan_flag):
+        out[0] = x.abs().max() if not torch.isnan(x).any() else float("nan")
+        if torch.isnan(x).any():
+            nan_flag[0] = 1
+
+    @staticmethod
+    def bmuf_update(glob, local, delta_prev, delta_sum, world, bm, blr):
+        d = delta_sum / float(world)
+        delta_prev.copy_(bm * delta_prev + blr * (1 - bm) * d)
+        glob.sub_((1 + bm) * delta_prev)
+        local.copy_(glob)
+
+
+def worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from oracle import train as ot
+    from pika_b200.trainer.bmuf import BmufTrainer, SUCCESS, STOP
+    torch.manual_seed(100 + rank)                      # ranks start from DIFFERENT weights: rank 0's must win
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+    w0 = [torch.nn.utils.parameters_to_vector(model.parameters()).detach().clone()]
+    bm, blr = 0.9, 1.0
+    tr = BmufTrainer(0, rank, world, model, bm, blr, backend="gloo", ops=NumpyOps)
+    flat0 = tr.param.clone()
+    # every rank now holds rank 0's initial parameters, and the model's parameters are views of the flat buffer
+    gathered = [torch.zeros_like(flat0) for _ in range(world)]
+    dist.all_gather(gathered, tr.flat.data.clone())
+    same_init = all(torch.equal(g, gathered[0]) for g in gathered)
+    views_ok = all(p.data_ptr() >= tr.flat.data.data_ptr() for p in model.parameters())
+    # two block syncs with rank-specific local updates, checked against the oracle formula
+    glob = flat0.numpy().astype(np.float64).copy()
+    dprev = np.zeros_like(glob)
+    ok = True
+    for it in range(2):
+        g = torch.Generator().manual_seed(7 * it + rank)
+        with torch.no_grad():
+            tr.flat.data.add_(0.01 * torch.randn(tr.flat.data.shape, generator=g))
+        locals_ = [torch.zeros_like(flat0) for _ in range(world)]
+        dist.all_gather(locals_, tr.flat.data.clone())
+        assert tr.update_and_sync() == SUCCESS
+        glob, dprev = ot.bmuf_update(glob, [l.numpy().astype(np.float64) for l in locals_], dprev, bm, blr)
+        ok &= np.allclose(tr.param.numpy(), glob, atol=1e-6) and torch.equal(tr.param, tr.flat.data)
+    # helper collectives
+    t = torch.tensor([float(rank + 1), 10.0])
+    tr.sum_reduce(t)
+    tr.broadcast(t)
+    helpers_ok = abs(t[0].item() - sum(range(1, world + 1))) < 1e-6
+    # collective NaN stop: only rank 1 diverges, EVERY rank must return STOP (no hang)
+    if rank == 1:
+        with torch.no_grad():
+            tr.flat.data[3] = float("nan")
+    stop = tr.update_and_sync()
+    q.put((rank, same_init, views_ok, bool(ok), helpers_ok, stop == STOP))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_bmuf_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(30)
+    for r in res:
+        assert all(r[1:]), r
