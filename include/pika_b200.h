@@ -223,6 +223,20 @@ int pk_beam_advance(const float* word_probs, const int* t_idx, const int* num_fr
 int pk_beam_reorder(const int* prev_k, const void* h_in, const float* c_in, const int* t_in, void* h_out, float* c_out,
                     int* t_out, int dtype, int K, int H, int layers, int rows, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Persistent LSTM layer (pika_b200/csrc/lstm_seq.cu): the whole recurrence of one nn.LSTM layer in one
+ * cooperative launch (trainer/model/transducer.py:56-61,95).  B <= 32 sequences, zero initial state.
+ *   fwd: gx f32 [B,U,4H] = x W_ih^T + b_ih + b_hh; w_hh bf16 [4H,H]; out [B,U,H] (f32|bf16);
+ *        gates_save f32 [U,B,4H], cs f32 [U,B,H] are kept for the backward.
+ *   bwd: dout [B,U,H] -> dG bf16 [U,B,4H] (gradient w.r.t. the pre-activation gates, time-major).
+ *   ws : pk_lstm_seq_workspace_bytes(H) bytes of scratch (grid barrier + hidden-state exchange).
+ */
+long long pk_lstm_seq_workspace_bytes(int H);
+int pk_lstm_seq_fwd(const float* gx, const void* w_hh_bf16, void* out, int out_dtype, float* gates_save, float* cs, int B,
+                    int U, int H, void* ws, void* stream);
+int pk_lstm_seq_bwd(const void* dout, int dtype, const float* gates_save, const float* cs, const void* w_hh_bf16, void* dG_bf16,
+                    int B, int U, int H, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,250 @@
+// Persistent LSTM layer kernels: the whole time recurrence (forward, and back-propagation through time)
+// runs inside ONE cooperative launch instead of two launches per step.
+//
+// Replaces cuDNN's nn.LSTM recurrence (trainer/model/transducer.py:56-61,95) for the prediction net.
+//
+// Work split: the hidden units are sharded across the CTAs (HJ = 8 units per CTA -> H/8 = 128 CTAs for
+// H = 1024, one per SM).  A CTA keeps its slice of the recurrent weights resident in shared memory for all U
+// steps: forward the 4*HJ gate rows W_hh[g*H + j, :], backward the transposed columns W_hh[:, j].  Per step
+// every CTA reads the full previous hidden state (forward, 64 KB) or the full gate-gradient row block
+// (backward, 256 KB) from L2, multiplies it against its resident slice on the tensor cores, applies the fused
+// cell update for its (batch, unit) pairs, publishes its slice, and the grid meets at a barrier.
+//
+// The batch is tiny (<= 32 rows = two m16 tiles) and the op is latency-bound, so the products use the
+// warp-level mma.sync.m16n8k16 path: a tcgen05 tile needs M >= 64 rows and a TMEM round trip per step, which
+// would more than double the per-step latency for no throughput benefit.  (Every throughput-bound contraction
+// of the model goes through the tcgen05 kernel in gemm.cu, including this layer's input projection, dW_ih,
+// dW_hh and dx.)  bf16 operands, fp32 accumulation and state.
+#include <cooperative_groups.h>
+
+#include "../../include/pika_b200.h"
+#include "common.cuh"
+
+namespace pk {
+void count_launch();
+
+constexpr int LS_HJ = 8;          // hidden units per CTA
+constexpr int LS_MB = 32;         // batch rows per launch
+constexpr int LS_THREADS = 256;
+constexpr int LS_PAD = 8;         // bf16 elements of row padding (bank-conflict-free fragment loads)
+
+PK_DEVICE void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+PK_DEVICE uint4 ldcg16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+PK_DEVICE void grid_barrier(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+PK_DEVICE float sigm(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------ forward
+// gx [B,U,4H] f32 (input projection + both biases); w_hh bf16 [4H,H]; out (T) [B,U,H]; hx bf16 [2,32,H] exchange;
+// gates_save f32 [U,B,4H] (post-activation i,f,g,o), cs f32 [U,B,H].
+template <typename T>
+__global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ w_hh,
+                                                                     T* __restrict__ out, __nv_bfloat16* hx, float* __restrict__ gates_save,
+                                                                     float* __restrict__ cs, int B, int U, int H, unsigned int* counter) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int P = H + LS_PAD;
+    __nv_bfloat16* w_s = reinterpret_cast<__nv_bfloat16*>(sm_raw);               // [32][P]: row g*8+jj = W_hh[g*H + j0 + jj]
+    __nv_bfloat16* h_s = w_s + 32 * P;                                           // [32][P]: h_{t-1}
+    float* g_s = reinterpret_cast<float*>(h_s + 32 * P);                         // [32][33]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int j0 = blockIdx.x * LS_HJ;
+    const int vec_per_row = H / 8;
+    for (int i = tid; i < 32 * vec_per_row; i += LS_THREADS) {
+        const int r = i / vec_per_row, v = i - r * vec_per_row;
+        const int grow = (r >> 3) * H + j0 + (r & 7);
+        *reinterpret_cast<uint4*>(w_s + r * P + v * 8) = *reinterpret_cast<const uint4*>(w_hh + (long long)grow * H + v * 8);
+    }
+    const int cb = tid >> 3, cj = tid & 7;                                      // cell ownership: batch row, local unit
+    float c_state = 0.f;
+    const int mt = warp & 1, nt = warp >> 1;                                    // 2 m-tiles x 4 n-tiles of the [32 x 32] product
+    const int g = lane >> 2, tq = lane & 3;
+    __syncthreads();
+    for (int t = 0; t < U; ++t) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (t > 0) {
+            const __nv_bfloat16* src = hx + (long long)((t - 1) & 1) * LS_MB * H;
+            for (int i = tid; i < 32 * vec_per_row; i += LS_THREADS) {
+                const int r = i / vec_per_row, v = i - r * vec_per_row;
+                *reinterpret_cast<uint4*>(h_s + r * P + v * 8) = ldcg16(src + (long long)r * H + v * 8);
+            }
+            __syncthreads();
+            const __nv_bfloat16* ar0 = h_s + (mt * 16 + g) * P + 2 * tq;
+            const __nv_bfloat16* ar1 = ar0 + 8 * P;
+            const __nv_bfloat16* br = w_s + (nt * 8 + g) * P + 2 * tq;
+#pragma unroll 8
+            for (int k0 = 0; k0 < H; k0 += 16) {
+                const uint32_t a0 = *reinterpret_cast<const uint32_t*>(ar0 + k0), a1 = *reinterpret_cast<const uint32_t*>(ar1 + k0);
+                const uint32_t a2 = *reinterpret_cast<const uint32_t*>(ar0 + k0 + 8), a3 = *reinterpret_cast<const uint32_t*>(ar1 + k0 + 8);
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(br + k0), b1 = *reinterpret_cast<const uint32_t*>(br + k0 + 8);
+                mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
+            }
+        }
+        g_s[(mt * 16 + g) * 33 + nt * 8 + 2 * tq] = acc[0];
+        g_s[(mt * 16 + g) * 33 + nt * 8 + 2 * tq + 1] = acc[1];
+        g_s[(mt * 16 + g + 8) * 33 + nt * 8 + 2 * tq] = acc[2];
+        g_s[(mt * 16 + g + 8) * 33 + nt * 8 + 2 * tq + 1] = acc[3];
+        __syncthreads();
+        // fused cell for (cb, j0 + cj); local gate rows: i = cj, f = 8 + cj, g = 16 + cj, o = 24 + cj
+        if (cb < B) {
+            const float* gxr = gx + ((long long)cb * U + t) * 4 * H + j0 + cj;
+            const float gi = sigm(g_s[cb * 33 + cj] + gxr[0]);
+            const float gf = sigm(g_s[cb * 33 + 8 + cj] + gxr[H]);
+            const float gg = tanhf(g_s[cb * 33 + 16 + cj] + gxr[2 * H]);
+            const float go = sigm(g_s[cb * 33 + 24 + cj] + gxr[3 * H]);
+            c_state = gf * c_state + gi * gg;
+            const float hv = go * tanhf(c_state);
+            out[((long long)cb * U + t) * H + j0 + cj] = from_f32<T>(hv);
+            hx[(long long)(t & 1) * LS_MB * H + (long long)cb * H + j0 + cj] = __float2bfloat16_rn(hv);
+            float* gs = gates_save + ((long long)t * B + cb) * 4 * H + j0 + cj;
+            gs[0] = gi; gs[H] = gf; gs[2 * H] = gg; gs[3 * H] = go;
+            cs[((long long)t * B + cb) * H + j0 + cj] = c_state;
+        } else {
+            hx[(long long)(t & 1) * LS_MB * H + (long long)cb * H + j0 + cj] = __float2bfloat16_rn(0.f);
+        }
+        if (t + 1 < U) grid_barrier(counter, (unsigned int)(gridDim.x * (t + 1)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// dout (T) [B,U,H]; gates_save, cs as saved by the forward; w_hh bf16 [4H,H];
+// dG bf16 [U,B,4H] (gradient w.r.t. the pre-activation gates, time-major: feeds dW_ih / dW_hh / dx GEMMs).
+template <typename T>
+__global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __restrict__ dout, const float* __restrict__ gates_save,
+                                                                     const float* __restrict__ cs, const __nv_bfloat16* __restrict__ w_hh,
+                                                                     __nv_bfloat16* dG, int B, int U, int H, unsigned int* counter) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int G4 = 4 * H;
+    const int PW = G4 + LS_PAD;                                                  // Wt_s pitch
+    const int KH = G4 / 2;                                                       // K half processed per phase
+    const int PD = KH + LS_PAD;
+    __nv_bfloat16* wt_s = reinterpret_cast<__nv_bfloat16*>(sm_raw);              // [8][PW]: wt_s[jj][r] = W_hh[r][j0+jj]
+    __nv_bfloat16* d_s = wt_s + LS_HJ * PW;                                      // [32][PD]: dG_{t+1}[:, half]
+    float* r_s = reinterpret_cast<float*>(d_s + 32 * PD);                        // [32][9] dh_rec
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int j0 = blockIdx.x * LS_HJ;
+    for (int i = tid; i < G4 * LS_HJ; i += LS_THREADS) {
+        const int r = i / LS_HJ, jj = i - r * LS_HJ;
+        wt_s[jj * PW + r] = w_hh[(long long)r * H + j0 + jj];
+    }
+    const int cb = tid >> 3, cj = tid & 7;
+    float dc_state = 0.f;
+    const int mt = warp & 1, kg = warp >> 1;                                     // 2 m-tiles x 4 K-groups
+    const int g = lane >> 2, tq = lane & 3;
+    const int vec_per_half = KH / 8;
+    __syncthreads();
+    for (int t = U - 1; t >= 0; --t) {
+        for (int i = tid; i < 32 * 9; i += LS_THREADS) r_s[i] = 0.f;
+        if (t < U - 1) {
+            const __nv_bfloat16* src = dG + (long long)(t + 1) * B * G4;
+            for (int half = 0; half < 2; ++half) {
+                __syncthreads();                                                // previous phase done with d_s / r_s zeroed
+                for (int i = tid; i < 32 * vec_per_half; i += LS_THREADS) {
+                    const int r = i / vec_per_half, v = i - r * vec_per_half;
+                    uint4 q = make_uint4(0, 0, 0, 0);
+                    if (r < B) q = ldcg16(src + (long long)r * G4 + half * KH + v * 8);
+                    *reinterpret_cast<uint4*>(d_s + r * PD + v * 8) = q;
+                }
+                __syncthreads();
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const int kspan = KH / 4;                                       // per K-group
+                const __nv_bfloat16* ar0 = d_s + (mt * 16 + g) * PD + kg * kspan + 2 * tq;
+                const __nv_bfloat16* ar1 = ar0 + 8 * PD;
+                const __nv_bfloat16* br = wt_s + g * PW + half * KH + kg * kspan + 2 * tq;
+#pragma unroll 8
+                for (int k0 = 0; k0 < kspan; k0 += 16) {
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(ar0 + k0), a1 = *reinterpret_cast<const uint32_t*>(ar1 + k0);
+                    const uint32_t a2 = *reinterpret_cast<const uint32_t*>(ar0 + k0 + 8), a3 = *reinterpret_cast<const uint32_t*>(ar1 + k0 + 8);
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(br + k0), b1 = *reinterpret_cast<const uint32_t*>(br + k0 + 8);
+                    mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
+                }
+                atomicAdd(&r_s[(mt * 16 + g) * 9 + 2 * tq], acc[0]);
+                atomicAdd(&r_s[(mt * 16 + g) * 9 + 2 * tq + 1], acc[1]);
+                atomicAdd(&r_s[(mt * 16 + g + 8) * 9 + 2 * tq], acc[2]);
+                atomicAdd(&r_s[(mt * 16 + g + 8) * 9 + 2 * tq + 1], acc[3]);
+            }
+        }
+        __syncthreads();
+        if (cb < B) {
+            const int j = j0 + cj;
+            const float* gs = gates_save + ((long long)t * B + cb) * G4 + j;
+            const float gi = gs[0], gf = gs[H], gg = gs[2 * H], go = gs[3 * H];
+            const float c = cs[((long long)t * B + cb) * H + j];
+            const float cp = t > 0 ? cs[((long long)(t - 1) * B + cb) * H + j] : 0.f;
+            const float dh = to_f32<T>(dout[((long long)cb * U + t) * H + j]) + r_s[cb * 9 + cj];
+            const float tc = tanhf(c);
+            const float dc = dh * go * (1.f - tc * tc) + dc_state;
+            __nv_bfloat16* d = dG + ((long long)t * B + cb) * G4 + j;
+            d[0] = __float2bfloat16_rn(dc * gg * gi * (1.f - gi));
+            d[H] = __float2bfloat16_rn(dc * cp * gf * (1.f - gf));
+            d[2 * H] = __float2bfloat16_rn(dc * gi * (1.f - gg * gg));
+            d[3 * H] = __float2bfloat16_rn(dh * tc * go * (1.f - go));
+            dc_state = dc * gf;
+        }
+        if (t > 0) grid_barrier(counter, (unsigned int)(gridDim.x * (U - t)));
+    }
+}
+}  // namespace pk
+
+using namespace pk;
+
+static int lstm_seq_check(int B, int U, int H) {
+    PK_CHECK_ARG(B >= 1 && B <= LS_MB, "persistent LSTM handles at most 32 sequences per launch");
+    PK_CHECK_ARG(U >= 1 && H % 64 == 0 && H / LS_HJ <= num_sms(), "H must be a multiple of 64 with H/8 <= #SMs");
+    return 0;
+}
+extern "C" long long pk_lstm_seq_workspace_bytes(int H) { return 2ll * LS_MB * H * 2 + 256; }
+
+/* ws: pk_lstm_seq_workspace_bytes(H): [barrier counter (256 B)] [hx bf16 2 x 32 x H] */
+extern "C" int pk_lstm_seq_fwd(const float* gx, const void* w_hh_bf16, void* out, int out_dtype, float* gates_save, float* cs, int B,
+                               int U, int H, void* ws, void* stream) {
+    int rc = lstm_seq_check(B, U, H);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
+    __nv_bfloat16* hx = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(ws) + 256);
+    PK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    const int smem = 2 * 32 * (H + LS_PAD) * 2 + 32 * 33 * 4;
+    const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
+    void* args[] = {(void*)&gx, (void*)&w, (void*)&out, (void*)&hx, (void*)&gates_save, (void*)&cs, (void*)&B, (void*)&U, (void*)&H, (void*)&counter};
+    const void* fn = out_dtype == PK_BF16 ? (const void*)lstm_seq_fwd_kernel<__nv_bfloat16> : (const void*)lstm_seq_fwd_kernel<float>;
+    PK_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PK_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(H / LS_HJ), dim3(LS_THREADS), args, smem, st));
+    count_launch();
+    return 0;
+}
+extern "C" int pk_lstm_seq_bwd(const void* dout, int dtype, const float* gates_save, const float* cs, const void* w_hh_bf16, void* dG_bf16,
+                               int B, int U, int H, void* ws, void* stream) {
+    int rc = lstm_seq_check(B, U, H);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
+    PK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    const int G4 = 4 * H;
+    const int smem = LS_HJ * (G4 + LS_PAD) * 2 + 32 * (G4 / 2 + LS_PAD) * 2 + 32 * 9 * 4;
+    const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
+    __nv_bfloat16* dg = reinterpret_cast<__nv_bfloat16*>(dG_bf16);
+    void* args[] = {(void*)&dout, (void*)&gates_save, (void*)&cs, (void*)&w, (void*)&dg, (void*)&B, (void*)&U, (void*)&H, (void*)&counter};
+    const void* fn = dtype == PK_BF16 ? (const void*)lstm_seq_bwd_kernel<__nv_bfloat16> : (const void*)lstm_seq_bwd_kernel<float>;
+    PK_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PK_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(H / LS_HJ), dim3(LS_THREADS), args, smem, st));
+    count_launch();
+    return 0;
+}

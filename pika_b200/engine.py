@@ -416,8 +416,12 @@ class LstmLayerFn(torch.autograd.Function):
         out = _new((B, U, H), like=x)
         gates = torch.empty(U, B, 4 * H, dtype=torch.float32, device=x.device)
         cs = torch.empty(U, B, H, dtype=torch.float32, device=x.device)
+        ctx.persistent = (x.dtype == torch.bfloat16 and B <= 32 and H % 64 == 0 and H // 8 <= 148)
+        if ctx.persistent:
+            # whole recurrence in one cooperative launch (pika_b200/csrc/lstm_seq.cu)
+            K.lstm_seq_fwd(gx, whh_parts[0], out, gates, cs)
         gh = torch.empty(B, 4 * H, dtype=torch.float32, device=x.device)
-        for t in range(U):
+        for t in range(0 if not ctx.persistent else U, U):
             if t > 0:
                 gemm_parts([stage_act_view(out[:, t - 1, :])], [whh_parts], gh, block_n=64)
             K.lstm_cell_fwd(gx[:, t, :], gh if t > 0 else None, cs[t - 1] if t > 0 else None, cs[t], out[:, t, :], gates[t], B, H)
@@ -436,7 +440,9 @@ class LstmLayerFn(torch.autograd.Function):
         dG = _new((U, B, 4 * H), like=out)                 # time-major: dG[t] is a contiguous [B,4H] matrix
         dh_rec = torch.empty(B, H, dtype=torch.float32, device=x.device)
         dc = [torch.empty(B, H, dtype=torch.float32, device=x.device) for _ in range(2)]
-        for t in range(U - 1, -1, -1):
+        if ctx.persistent:
+            K.lstm_seq_bwd(dout, gates, cs, ctx.whh_parts[0], dG)
+        for t in range(U - 1 if not ctx.persistent else -1, -1, -1):
             last = (t == U - 1)
             K.lstm_cell_bwd(dout[:, t, :], None if last else dh_rec, None if last else dc[(t + 1) & 1], gates[t], cs[t],
                             cs[t - 1] if t > 0 else None, dG[t], dc[t & 1], B, H)

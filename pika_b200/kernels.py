@@ -250,3 +250,29 @@ def bmuf_delta(glob, local, delta):
 def bmuf_update(glob, local, delta_prev, delta_sum, world, bm, blr):
     check(lib.pk_bmuf_update(_P(glob), _P(local), _P(delta_prev), _P(delta_sum), _L(glob.numel()), _I(world), _F(bm), _F(blr),
                              _stream()), "pk_bmuf_update")
+
+
+_lstm_ws = {}
+
+
+def _lstm_scratch(H, device):
+    key = (H, str(device))
+    if key not in _lstm_ws:
+        lib.pk_lstm_seq_workspace_bytes.restype = ctypes.c_longlong
+        _lstm_ws[key] = torch.zeros(int(lib.pk_lstm_seq_workspace_bytes(H)), dtype=torch.uint8, device=device)
+    return _lstm_ws[key]
+
+
+def lstm_seq_fwd(gx, w_hh, out, gates_save, cs):
+    B, U, G4 = gx.shape
+    H = G4 // 4
+    assert gx.is_contiguous() and out.is_contiguous() and w_hh.dtype == torch.bfloat16 and w_hh.is_contiguous()
+    check(lib.pk_lstm_seq_fwd(_P(gx), _P(w_hh), _P(out), _I(_dt(out)), _P(gates_save), _P(cs), _I(B), _I(U), _I(H),
+                              _P(_lstm_scratch(H, gx.device)), _stream()), "pk_lstm_seq_fwd")
+
+
+def lstm_seq_bwd(dout, gates_save, cs, w_hh, dG):
+    B, U, H = dout.shape
+    assert dout.is_contiguous() and dG.dtype == torch.bfloat16 and dG.is_contiguous()
+    check(lib.pk_lstm_seq_bwd(_P(dout), _I(_dt(dout)), _P(gates_save), _P(cs), _P(w_hh), _P(dG), _I(B), _I(U), _I(H),
+                              _P(_lstm_scratch(H, dout.device)), _stream()), "pk_lstm_seq_bwd")

@@ -277,3 +277,36 @@ def test_dropout_linear_backward_uses_forward_mask():
     (gx2,) = torch.autograd.grad(ref2, [x2], dy)
     y2.backward(dy)
     assert rel(x2.grad, gx2) < TOL
+
+
+@pytest.mark.parametrize("B,U,H", [(5, 12, 128), (32, 40, 256)])
+def test_lstm_persistent_kernel_bf16(B, U, H):
+    """bf16 production path: the cooperative persistent LSTM kernels (lstm_seq.cu) vs torch fp32 nn.LSTM with
+    bf16-rounded weights; bf16 activations/recurrent operands -> 2e-2 outputs, 6e-2 gradients (norm-relative)."""
+    from pika_b200 import engine as E
+    E.set_precision("bf16")
+    V, Ed = 30, 100
+    emb = nn.Embedding(V + 1, Ed, padding_idx=V).cuda()
+    lstm = nn.LSTM(Ed, H, num_layers=2, batch_first=True, dropout=0.0).cuda()
+    with torch.no_grad():
+        for p in list(lstm.parameters()) + [emb.weight]:
+            p.copy_(p.to(torch.bfloat16).float())
+    y = torch.randint(1, V, (B, U), device="cuda")
+
+    class M(nn.Module):
+        pass
+    m = M(); m.embed = emb; m.decoder = lstm
+    lstm.train()
+    out = E.prednet_forward_act(m, y)
+    assert out.dtype == torch.bfloat16
+    yy = torch.cat((torch.zeros(B, 1, dtype=torch.long, device="cuda"), y), 1)
+    ref, _ = lstm(emb(yy))
+    assert rel(out, ref) < 2e-2
+    dy = g(B, U + 1, H, seed=40)
+    params = [emb.weight] + list(lstm.parameters())
+    gs = torch.autograd.grad(ref, params, dy)
+    for p in params:
+        p.grad = None
+    out.backward(dy.to(torch.bfloat16))
+    for p, gr, name in zip(params, gs, ["emb"] + [n for n, _ in lstm.named_parameters()]):
+        assert rel(p.grad, gr) < 6e-2, (name, rel(p.grad, gr))
