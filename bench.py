@@ -192,7 +192,7 @@ def run_ours(a):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="nccl", init_method="env://")
+        dist.init_process_group(backend="nccl", init_method="env://", device_id=dev)
     from pika_b200 import engine, _lib
     from pika_b200.frontend import FbankOptions, Frontend
     from pika_b200.model.transducer import Net
@@ -279,6 +279,9 @@ def run_ours(a):
     e2e = world * B * a.steps / (ms_e2e / 1e3)
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     hbm, tf_burst, tf_sus, src = peaks()
     # ---- live roofline of the dominant kernel: the fc2 joint GEMM (forward shape), timed alone with CUDA events
@@ -332,6 +335,9 @@ def run_ours(a):
         except Exception as ex:                                   # the baseline is reported, never required
             res["cpu_baseline"] = {"error": repr(ex)}
     print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -102,11 +102,13 @@ int pk_gemm_bf16(const pk_gemm_desc* desc, void* stream);
  *   costs   [B] f32 = -log P(y_n | x_n)
  *   dlogits same shape/dtype as logits, may alias it (in place); NULL = loss only.
  *           Entries of padded nodes and of the row padding [V, ldv) are written as 0.
+ *   dlogits_colsum [ldv] f32 or NULL: sum of dlogits over all (b,t,u) rows = the joint fc2 bias gradient,
+ *           produced by the gradient pass itself (each thread owns fixed columns), so dlogits is not re-read.
  */
 long long pk_rnnt_loss_workspace_bytes(int B, int T, int U1);
 int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const int* frame_lens,
                          const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
-                         const float* grad_scale, float* costs, void* dlogits, void* workspace,
+                         const float* grad_scale, float* costs, void* dlogits, float* dlogits_colsum, void* workspace,
                          long long workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -151,7 +153,9 @@ int pk_log_softmax(const void* x, int dtype, long long ld, float* y, long long r
 /* gated joint, factored: h[b,t,u,:] = tanh(e1[b,t]+p1[b,u]) * sigmoid(eg[b,t]+pg[b,u])
  * (trainer/model/transducer.py:102-108 without materialising the 2H-wide concat).
  * ex [B*T, 2H], py [B*U1, 2H] = the x / y halves of fc1 | fc_gate applied to encoder / prediction outputs. */
-int pk_joint_gate_fwd(const void* ex, const void* py, void* h, int dtype, int B, int T, int U1, int H, void* stream);
+/* h has row pitch ld_h = H or H+8; with H+8 the pad columns are written as (1,0,..,0) so that the fc2 bias gradient
+ * falls out of the fc2 wgrad GEMM as one extra column */
+int pk_joint_gate_fwd(const void* ex, const void* py, void* h, int dtype, int B, int T, int U1, int H, int ld_h, void* stream);
 int pk_joint_gate_bwd(const void* ex, const void* py, const void* dh, void* dex, void* dpy, int dtype, int B, int T, int U1,
                       int H, void* stream);
 /* one LSTM time step, pointwise part (nn.LSTM, gate order i,f,g,o; trainer/model/transducer.py:56-61) */

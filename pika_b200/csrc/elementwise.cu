@@ -471,8 +471,9 @@ template <> PK_DEVICE float jt_sigmoid<__nv_bfloat16>(float x) { return fmaf(jt_
 
 template <typename T>
 __global__ void __launch_bounds__(128) joint_gate_fwd_kernel(const T* __restrict__ ex, const T* __restrict__ py, T* __restrict__ h,
-                                                             int B, int Tt, int U1, int H) {
-    // one CTA per (b,t); threads over channels (8 each); loop over u
+                                                             int B, int Tt, int U1, int H, int ld_h) {
+    // one CTA per (b,t); threads over channels (8 each); loop over u.  When ld_h > H the 8 pad columns hold
+    // (1, 0, ..., 0): the ones column turns the fc2 bias gradient into one extra column of the wgrad GEMM.
     const int bt = blockIdx.x;
     const int b = bt / Tt;
     for (int c0 = threadIdx.x * 8; c0 < H; c0 += blockDim.x * 8) {
@@ -486,7 +487,13 @@ __global__ void __launch_bounds__(128) joint_gate_fwd_kernel(const T* __restrict
             V8<T>::load(pr + H + c0, pg);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = jt_tanh<T>(e1[e] + p1[e]) * jt_sigmoid<T>(eg[e] + pg[e]);
-            V8<T>::store(h + ((long long)bt * U1 + u) * H + c0, o);
+            V8<T>::store(h + ((long long)bt * U1 + u) * ld_h + c0, o);
+        }
+    }
+    if (ld_h > H) {
+        for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+            const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            V8<T>::store(h + ((long long)bt * U1 + u) * ld_h + H, one);
         }
     }
 }
@@ -760,9 +767,9 @@ extern "C" int pk_log_softmax(const void* x, int dtype, long long ld, float* y, 
     DONE();
 }
 
-extern "C" int pk_joint_gate_fwd(const void* ex, const void* py, void* h, int dtype, int B, int T_, int U1, int H, void* stream) {
-    PK_CHECK_ARG(H % 8 == 0, "H must be a multiple of 8");
-    PK_DISPATCH_T(dtype, (joint_gate_fwd_kernel<T><<<B * T_, 128, 0, STREAM(stream)>>>((const T*)ex, (const T*)py, (T*)h, B, T_, U1, H)));
+extern "C" int pk_joint_gate_fwd(const void* ex, const void* py, void* h, int dtype, int B, int T_, int U1, int H, int ld_h, void* stream) {
+    PK_CHECK_ARG(H % 8 == 0 && (ld_h == H || ld_h == H + 8), "H % 8 == 0 and ld_h in {H, H+8}");
+    PK_DISPATCH_T(dtype, (joint_gate_fwd_kernel<T><<<B * T_, 128, 0, STREAM(stream)>>>((const T*)ex, (const T*)py, (T*)h, B, T_, U1, H, ld_h)));
     DONE();
 }
 extern "C" int pk_joint_gate_bwd(const void* ex, const void* py, const void* dh, void* dex, void* dpy, int dtype, int B, int T_, int U1,

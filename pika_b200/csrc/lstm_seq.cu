@@ -39,6 +39,14 @@ PK_DEVICE uint4 ldcg16(const void* p) {
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// 1-D bulk async copy global -> shared (TMA engine, no register staging), completion on an mbarrier
+PK_DEVICE void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+PK_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 PK_DEVICE void grid_barrier(unsigned int* counter, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -76,16 +84,23 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float
     float c_state = 0.f;
     const int mt = warp & 1, nt = warp >> 1;                                    // 2 m-tiles x 4 n-tiles of the [32 x 32] product
     const int g = lane >> 2, tq = lane & 3;
+    __shared__ __align__(8) uint64_t h_bar;
+    if (tid == 0) { mbar_init(&h_bar, 1); mbar_fence_init(); }
+    uint32_t h_phase = 0;
     __syncthreads();
     for (int t = 0; t < U; ++t) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         if (t > 0) {
+            // all-gather of h_{t-1} (32 x H bf16) from L2 by the TMA engine: lane r of warp 0 copies row r
             const __nv_bfloat16* src = hx + (long long)((t - 1) & 1) * LS_MB * H;
-            for (int i = tid; i < 32 * vec_per_row; i += LS_THREADS) {
-                const int r = i / vec_per_row, v = i - r * vec_per_row;
-                *reinterpret_cast<uint4*>(h_s + r * P + v * 8) = ldcg16(src + (long long)r * H + v * 8);
+            if (warp == 0) {
+                fence_proxy_async_all();
+                if (lane == 0) mbar_arrive_expect_tx(&h_bar, 32u * (uint32_t)H * 2u);
+                __syncwarp();
+                bulk_g2s(h_s + lane * P, src + (long long)lane * H, (uint32_t)H * 2u, &h_bar);
             }
-            __syncthreads();
+            mbar_wait(&h_bar, h_phase);
+            h_phase ^= 1;
             const __nv_bfloat16* ar0 = h_s + (mt * 16 + g) * P + 2 * tq;
             const __nv_bfloat16* ar1 = ar0 + 8 * P;
             const __nv_bfloat16* br = w_s + (nt * 8 + g) * P + 2 * tq;
@@ -133,41 +148,48 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
     extern __shared__ __align__(16) uint8_t sm_raw[];
     const int G4 = 4 * H;
     const int PW = G4 + LS_PAD;                                                  // Wt_s pitch
-    const int KH = G4 / 2;                                                       // K half processed per phase
-    const int PD = KH + LS_PAD;
+    const int KQ = G4 / 4;                                                       // K quarter per pipeline stage
+    const int PD = KQ + LS_PAD;
     __nv_bfloat16* wt_s = reinterpret_cast<__nv_bfloat16*>(sm_raw);              // [8][PW]: wt_s[jj][r] = W_hh[r][j0+jj]
-    __nv_bfloat16* d_s = wt_s + LS_HJ * PW;                                      // [32][PD]: dG_{t+1}[:, half]
-    float* r_s = reinterpret_cast<float*>(d_s + 32 * PD);                        // [32][9] dh_rec
+    __nv_bfloat16* d_s = wt_s + LS_HJ * PW;                                      // [2][32][PD]: quarters of dG_{t+1}, double-buffered
+    float* r_s = reinterpret_cast<float*>(d_s + 2 * 32 * PD);                    // [32][9] dh_rec
+    __shared__ __align__(8) uint64_t q_bar[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j0 = blockIdx.x * LS_HJ;
     for (int i = tid; i < G4 * LS_HJ; i += LS_THREADS) {
         const int r = i / LS_HJ, jj = i - r * LS_HJ;
         wt_s[jj * PW + r] = w_hh[(long long)r * H + j0 + jj];
     }
+    for (int i = tid; i < 2 * 32 * PD / 8; i += LS_THREADS) reinterpret_cast<uint4*>(d_s)[i] = make_uint4(0, 0, 0, 0);   // rows >= B stay zero
+    if (tid == 0) { mbar_init(&q_bar[0], 1); mbar_init(&q_bar[1], 1); mbar_fence_init(); }
     const int cb = tid >> 3, cj = tid & 7;
     float dc_state = 0.f;
     const int mt = warp & 1, kg = warp >> 1;                                     // 2 m-tiles x 4 K-groups
     const int g = lane >> 2, tq = lane & 3;
-    const int vec_per_half = KH / 8;
+    uint32_t q_phase[2] = {0, 0};
     __syncthreads();
     for (int t = U - 1; t >= 0; --t) {
         for (int i = tid; i < 32 * 9; i += LS_THREADS) r_s[i] = 0.f;
         if (t < U - 1) {
             const __nv_bfloat16* src = dG + (long long)(t + 1) * B * G4;
-            for (int half = 0; half < 2; ++half) {
-                __syncthreads();                                                // previous phase done with d_s / r_s zeroed
-                for (int i = tid; i < 32 * vec_per_half; i += LS_THREADS) {
-                    const int r = i / vec_per_half, v = i - r * vec_per_half;
-                    uint4 q = make_uint4(0, 0, 0, 0);
-                    if (r < B) q = ldcg16(src + (long long)r * G4 + half * KH + v * 8);
-                    *reinterpret_cast<uint4*>(d_s + r * PD + v * 8) = q;
+            auto issue = [&](int qtr) {                                          // warp 0: lane r copies row r of quarter `qtr`
+                if (warp == 0) {
+                    fence_proxy_async_all();
+                    if (lane == 0) mbar_arrive_expect_tx(&q_bar[qtr & 1], (uint32_t)B * (uint32_t)KQ * 2u);
+                    __syncwarp();
+                    if (lane < B) bulk_g2s(d_s + ((qtr & 1) * 32 + lane) * PD, src + (long long)lane * G4 + qtr * KQ, (uint32_t)KQ * 2u, &q_bar[qtr & 1]);
                 }
-                __syncthreads();
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                const int kspan = KH / 4;                                       // per K-group
-                const __nv_bfloat16* ar0 = d_s + (mt * 16 + g) * PD + kg * kspan + 2 * tq;
+            };
+            issue(0);
+            issue(1);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const int kspan = KQ / 4;                                            // per K-group
+            for (int qtr = 0; qtr < 4; ++qtr) {
+                mbar_wait(&q_bar[qtr & 1], q_phase[qtr & 1]);
+                q_phase[qtr & 1] ^= 1;
+                const __nv_bfloat16* ar0 = d_s + ((qtr & 1) * 32 + mt * 16 + g) * PD + kg * kspan + 2 * tq;
                 const __nv_bfloat16* ar1 = ar0 + 8 * PD;
-                const __nv_bfloat16* br = wt_s + g * PW + half * KH + kg * kspan + 2 * tq;
+                const __nv_bfloat16* br = wt_s + g * PW + qtr * KQ + kg * kspan + 2 * tq;
 #pragma unroll 8
                 for (int k0 = 0; k0 < kspan; k0 += 16) {
                     const uint32_t a0 = *reinterpret_cast<const uint32_t*>(ar0 + k0), a1 = *reinterpret_cast<const uint32_t*>(ar1 + k0);
@@ -175,11 +197,15 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
                     const uint32_t b0 = *reinterpret_cast<const uint32_t*>(br + k0), b1 = *reinterpret_cast<const uint32_t*>(br + k0 + 8);
                     mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
                 }
-                atomicAdd(&r_s[(mt * 16 + g) * 9 + 2 * tq], acc[0]);
-                atomicAdd(&r_s[(mt * 16 + g) * 9 + 2 * tq + 1], acc[1]);
-                atomicAdd(&r_s[(mt * 16 + g + 8) * 9 + 2 * tq], acc[2]);
-                atomicAdd(&r_s[(mt * 16 + g + 8) * 9 + 2 * tq + 1], acc[3]);
+                if (qtr + 2 < 4) {
+                    __syncthreads();                                             // every warp is done reading this buffer
+                    issue(qtr + 2);
+                }
             }
+            atomicAdd(&r_s[(mt * 16 + g) * 9 + 2 * tq], acc[0]);
+            atomicAdd(&r_s[(mt * 16 + g) * 9 + 2 * tq + 1], acc[1]);
+            atomicAdd(&r_s[(mt * 16 + g + 8) * 9 + 2 * tq], acc[2]);
+            atomicAdd(&r_s[(mt * 16 + g + 8) * 9 + 2 * tq + 1], acc[3]);
         }
         __syncthreads();
         if (cb < B) {
@@ -238,7 +264,7 @@ extern "C" int pk_lstm_seq_bwd(const void* dout, int dtype, const float* gates_s
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
     PK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
     const int G4 = 4 * H;
-    const int smem = LS_HJ * (G4 + LS_PAD) * 2 + 32 * (G4 / 2 + LS_PAD) * 2 + 32 * 9 * 4;
+    const int smem = LS_HJ * (G4 + LS_PAD) * 2 + 2 * 32 * (G4 / 4 + LS_PAD) * 2 + 32 * 9 * 4;
     const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
     __nv_bfloat16* dg = reinterpret_cast<__nv_bfloat16*>(dG_bf16);
     void* args[] = {(void*)&dout, (void*)&gates_save, (void*)&cs, (void*)&w, (void*)&dg, (void*)&B, (void*)&U, (void*)&H, (void*)&counter};

@@ -290,53 +290,108 @@ __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
 }
 
 // ------------------------------------------------------------------------------------ pass 3
+// One CTA walks a contiguous block of joint nodes; thread i owns the 16-byte column groups i, i+256, ... of every
+// row (GRAD_MAXG groups -> V <= 256*8*GRAD_MAXG for bf16), so the column sums of dlogits (= the fc2 bias
+// gradient) accumulate in registers for free.  GRAD_RU rows are in flight per thread.
+constexpr int GRAD_THREADS = 256;
+constexpr int GRAD_MAXG = 4;
+constexpr int GRAD_RU = 2;
 template <typename T>
-__global__ void __launch_bounds__(256) rnnt_grad_kernel(const T* logits, const int* __restrict__ labels,
-                                                        const int* __restrict__ label_lens, RnntDims d,
-                                                        const float* __restrict__ lse_in, const float* __restrict__ gb_in,
-                                                        const float* __restrict__ gl_in, T* dlogits) {
+__global__ void __launch_bounds__(GRAD_THREADS, 3) rnnt_grad_kernel(const T* logits, const int* __restrict__ labels,
+                                                                    const int* __restrict__ label_lens, RnntDims d,
+                                                                    const float* __restrict__ lse_in, const float* __restrict__ gb_in,
+                                                                    const float* __restrict__ gl_in, T* dlogits, float* __restrict__ colsum,
+                                                                    long long rows_per_cta) {
     constexpr int VN = Vec16<T>::N;
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    extern __shared__ float gsm[];                          // per-row scalars of this CTA's block: gb, gl, lse*log2e, label
+    float* s_gb = gsm;
+    float* s_gl = gsm + rows_per_cta;
+    float* s_l2 = gsm + 2 * rows_per_cta;
+    int* s_y = reinterpret_cast<int*>(gsm + 3 * rows_per_cta);
     const long long rows = (long long)d.B * d.T * d.U1;
-    const int nvec_ld = d.ldv / VN;            // also clears the row padding [V, ldv)
-    for (long long row = warp_global; row < rows; row += n_warps) {
-        const float gb = gb_in[row], gl = gl_in[row];
-        const uint4* vp = reinterpret_cast<const uint4*>(logits + row * (long long)d.ldv);
-        uint4* op = reinterpret_cast<uint4*>(dlogits + row * (long long)d.ldv);
-        if (gb == 0.f && gl == 0.f) {          // padded (or zero-probability) node: write zeros, read nothing
-            for (int i = lane; i < nvec_ld; i += 32) st_stream(op + i, make_uint4(0, 0, 0, 0));
-            continue;
-        }
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = min(rows, r0 + rows_per_cta);
+    const int nvec_ld = d.ldv / VN;
+    const int tid = threadIdx.x;
+    for (long long row = r0 + tid; row < r1; row += GRAD_THREADS) {
+        const int i = (int)(row - r0);
+        s_gb[i] = gb_in[row];
+        s_gl[i] = gl_in[row];
+        s_l2[i] = lse_in[row] * kLog2e;
         const int u = (int)(row % d.U1);
         const int b = (int)(row / ((long long)d.T * d.U1));
-        const int y = (u < label_lens[b]) ? labels[(size_t)b * d.ld_labels + u] : -1;
-        const float l2 = lse_in[row] * kLog2e;
-        const float gsum = -(gb + gl);          // softmax coefficient
-        for (int i0 = lane; i0 < nvec_ld; i0 += 32 * ROWSTATS_UNROLL) {
-            uint4 q[ROWSTATS_UNROLL];
+        s_y[i] = (u < label_lens[b]) ? labels[(size_t)b * d.ld_labels + u] : -1;
+    }
+    __syncthreads();
+    float cs[GRAD_MAXG][VN];
 #pragma unroll
-            for (int k = 0; k < ROWSTATS_UNROLL; ++k) {
-                const int i = i0 + k * 32;
-                if (i < nvec_ld) q[k] = ld_plain(vp + i);
+    for (int gq = 0; gq < GRAD_MAXG; ++gq)
+#pragma unroll
+        for (int e = 0; e < VN; ++e) cs[gq][e] = 0.f;
+    for (long long rb = r0; rb < r1; rb += GRAD_RU) {
+        uint4 q[GRAD_RU][GRAD_MAXG];
+#pragma unroll
+        for (int k = 0; k < GRAD_RU; ++k) {
+            const long long row = rb + k;
+            if (row < r1 && (s_gb[row - r0] != 0.f || s_gl[row - r0] != 0.f)) {
+                const uint4* vp = reinterpret_cast<const uint4*>(logits + row * (long long)d.ldv);
+#pragma unroll
+                for (int gq = 0; gq < GRAD_MAXG; ++gq) {
+                    const int i = tid + gq * GRAD_THREADS;
+                    if (i < nvec_ld) q[k][gq] = ld_plain(vp + i);
+                }
             }
+        }
 #pragma unroll
-            for (int k = 0; k < ROWSTATS_UNROLL; ++k) {
-                const int i = i0 + k * 32;
+        for (int k = 0; k < GRAD_RU; ++k) {
+            const long long row = rb + k;
+            if (row >= r1) continue;
+            const float gb = s_gb[row - r0], gl = s_gl[row - r0];
+            uint4* op = reinterpret_cast<uint4*>(dlogits + row * (long long)d.ldv);
+            if (gb == 0.f && gl == 0.f) {               // padded (or zero-probability) node: zeros, nothing read
+#pragma unroll
+                for (int gq = 0; gq < GRAD_MAXG; ++gq) {
+                    const int i = tid + gq * GRAD_THREADS;
+                    if (i < nvec_ld) st_stream(op + i, make_uint4(0, 0, 0, 0));
+                }
+                continue;
+            }
+            const int y = s_y[row - r0];
+            const float l2 = s_l2[row - r0];
+            const float gsum = -(gb + gl);
+#pragma unroll
+            for (int gq = 0; gq < GRAD_MAXG; ++gq) {
+                const int i = tid + gq * GRAD_THREADS;
                 if (i < nvec_ld) {
                     float f[VN];
-                    Vec16<T>::unpack(q[k], f);
+                    Vec16<T>::unpack(q[k][gq], f);
 #pragma unroll
                     for (int e = 0; e < VN; ++e) {
                         const int v = i * VN + e;
-                        float g = exp2f(f[e] * kLog2e - l2) * gsum;
-                        if (v == 0) g += gb;
-                        if (v == y) g += gl;
-                        f[e] = (v < d.V) ? g : 0.f;
+                        float gv = exp2f(f[e] * kLog2e - l2) * gsum;
+                        if (v == 0) gv += gb;
+                        if (v == y) gv += gl;
+                        f[e] = (v < d.V) ? gv : 0.f;
                     }
-                    st_stream(op + i, Vec16<T>::pack(f));
+                    const uint4 packed = Vec16<T>::pack(f);
+                    st_stream(op + i, packed);
+                    if (colsum) {                         // sum what was actually stored (bf16-rounded in production)
+                        float w[VN];
+                        Vec16<T>::unpack(packed, w);
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) cs[gq][e] += w[e];
+                    }
                 }
+            }
+        }
+    }
+    if (colsum) {
+#pragma unroll
+        for (int gq = 0; gq < GRAD_MAXG; ++gq) {
+            const int i = tid + gq * GRAD_THREADS;
+            if (i < nvec_ld) {
+#pragma unroll
+                for (int e = 0; e < VN; ++e) atomicAdd(&colsum[i * VN + e], cs[gq][e]);
             }
         }
     }
@@ -353,7 +408,7 @@ extern "C" long long pk_rnnt_loss_workspace_bytes(int B, int T, int U1) {
 
 extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const int* frame_lens,
                                     const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
-                                    const float* grad_scale, float* costs, void* dlogits, void* workspace,
+                                    const float* grad_scale, float* costs, void* dlogits, float* dlogits_colsum, void* workspace,
                                     long long workspace_bytes, void* stream_v) {
     using namespace pk;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
@@ -392,13 +447,21 @@ extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* la
                                                      costs, gb, gl);
     PK_CHECK_LAUNCH(); count_launch();
     if (dlogits != nullptr) {
+        PK_CHECK_ARG(ldv / vn <= GRAD_THREADS * GRAD_MAXG, "V too large for the gradient kernel (V <= 8192 bf16 / 4096 f32)");
+        if (dlogits_colsum) PK_CHECK_CUDA(cudaMemsetAsync(dlogits_colsum, 0, sizeof(float) * ldv, stream));
+        const int gcta = num_sms() * 12;
+        long long rpc = (rows + gcta - 1) / gcta;
+        rpc = (rpc + GRAD_RU - 1) / GRAD_RU * GRAD_RU;
+        if (rpc > 2048) rpc = 2048;                      // 16 bytes of shared memory per row
+        const int ggrid = (int)((rows + rpc - 1) / rpc);
+        const size_t gsmem = (size_t)rpc * 16;
         if (dtype == PK_BF16)
-            rnnt_grad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), labels,
-                                                                     label_lens, d, lse, gb, gl,
-                                                                     reinterpret_cast<__nv_bfloat16*>(dlogits));
+            rnnt_grad_kernel<__nv_bfloat16><<<ggrid, GRAD_THREADS, gsmem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), labels,
+                                                                              label_lens, d, lse, gb, gl,
+                                                                              reinterpret_cast<__nv_bfloat16*>(dlogits), dlogits_colsum, rpc);
         else
-            rnnt_grad_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(logits), labels, label_lens, d,
-                                                              lse, gb, gl, reinterpret_cast<float*>(dlogits));
+            rnnt_grad_kernel<float><<<ggrid, GRAD_THREADS, gsmem, stream>>>(reinterpret_cast<const float*>(logits), labels, label_lens, d,
+                                                                       lse, gb, gl, reinterpret_cast<float*>(dlogits), dlogits_colsum, rpc);
         PK_CHECK_LAUNCH(); count_launch();
     }
     return 0;

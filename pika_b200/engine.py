@@ -522,7 +522,7 @@ def _joint_forward(enc, pred, model):
     return logits, state
 
 
-def _joint_backward(dlogits, st, model, need_enc=True, need_pred=True):
+def _joint_backward(dlogits, st, model, need_enc=True, need_pred=True, db2=None):
     """dlogits [B,T,U1,ldv] (padding columns zero) -> (d_enc, d_pred); parameter grads written in place."""
     B, T, U1, H, V, ldv = st["dims"]
     R = B * T * U1
@@ -532,8 +532,9 @@ def _joint_backward(dlogits, st, model, need_enc=True, need_pred=True):
     dh = _new((R, H), like=dlogits)
     gemm_parts([dl_v], [st["w2"]], dh, b_mn=True)
     gemm_parts([dl_v], [st["h_parts"]], grad_of(fc2.weight), a_mn=True, b_mn=True)
-    db2 = torch.empty(ldv, dtype=torch.float32, device=dlogits.device)
-    K.colsum(dlogits.view(R, ldv), db2)
+    if db2 is None:
+        db2 = torch.empty(ldv, dtype=torch.float32, device=dlogits.device)
+        K.colsum(dlogits.view(R, ldv), db2)
     grad_of(fc2.bias).copy_(db2[:V])
     dex = _new((B * T, 2 * H), like=dlogits)
     dpy = _new((B * U1, 2 * H), like=dlogits)
@@ -585,8 +586,9 @@ class JointLossFn(torch.autograd.Function):
     def forward(ctx, enc, pred, model, labels, frame_lens, label_lens):
         logits, st = _joint_forward(enc, pred, model)
         V = st["dims"][4]
-        costs, _ = K.rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=V, dlogits=logits)
-        d_enc, d_pred = _joint_backward(logits, st, model)
+        db2 = torch.empty(logits.shape[-1], dtype=torch.float32, device=logits.device)
+        costs, _ = K.rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=V, dlogits=logits, colsum=db2)
+        d_enc, d_pred = _joint_backward(logits, st, model, db2=db2)
         del logits, st
         ctx.save_for_backward(d_enc, d_pred)
         return costs

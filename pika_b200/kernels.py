@@ -92,7 +92,7 @@ def gemm(a, b, c, a_mn=False, b_mn=False, a_sel=(SEL_ZB0, SEL_ZB1), b_sel=(SEL_Z
     return c
 
 
-def rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=None, grad_scale=None, dlogits=None, want_grad=True):
+def rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=None, grad_scale=None, dlogits=None, want_grad=True, colsum=None):
     """logits [B,T,U1,ldv] (bf16|f32) -> (costs [B] f32, dlogits).  dlogits may alias logits."""
     B, T, U1, ldv = logits.shape
     V = ldv if V is None else V
@@ -105,7 +105,7 @@ def rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=None, grad_scale
         dlogits = torch.empty_like(logits)
     check(lib.pk_rnnt_loss_fwd_bwd(_ptr(logits), _dt(logits), _ptr(labels), _ptr(frame_lens), _ptr(label_lens),
                                    B, T, U1, V, ldv, max(labels.stride(0), 1), _ptr(grad_scale), _ptr(costs),
-                                   _ptr(dlogits if want_grad else None), _ptr(ws), ws_bytes, _stream()),
+                                   _ptr(dlogits if want_grad else None), _ptr(colsum), _ptr(ws), ws_bytes, _stream()),
           "pk_rnnt_loss_fwd_bwd")
     return costs, dlogits
 
@@ -202,7 +202,8 @@ def log_softmax(x, y, n, scale=1.0):
 
 
 def joint_gate_fwd(ex, py, h, B, T, U1, H):
-    check(lib.pk_joint_gate_fwd(_P(ex), _P(py), _P(h), _I(_dt(ex)), _I(B), _I(T), _I(U1), _I(H), _stream()), "pk_joint_gate_fwd")
+    check(lib.pk_joint_gate_fwd(_P(ex), _P(py), _P(h), _I(_dt(ex)), _I(B), _I(T), _I(U1), _I(H), _I(h.stride(0)), _stream()),
+          "pk_joint_gate_fwd")
 
 
 def joint_gate_bwd(ex, py, dh, dex, dpy, B, T, U1, H):

@@ -1,0 +1,91 @@
+"""Native readers for the on-disk formats of the reference recipes (no PyKaldi):
+  * Kaldi int-vector archives ``ark:path`` / ``ark,t:path`` (labels; loader/otf_utt_loader.py:209 SequentialIntVectorReader)
+  * Kaldi text double matrix (global CMVN stats; trainer/train_transducer_bmuf_otfaug.py:341-346)
+  * ``.mrk`` / ``.seq`` raw-PCM shards (utils/wav_to_seq.py:36-38) and ``.lst`` triplets (loader/otf_utt_loader.py:124-129)
+"""
+import struct
+
+import numpy as np
+
+
+def parse_rspecifier(rspec):
+    if ":" in rspec and rspec.split(":", 1)[0].replace(",", "").replace("ark", "").replace("t", "").replace("scp", "") == "":
+        kind, path = rspec.split(":", 1)
+        if "scp" in kind:
+            raise NotImplementedError("scp rspecifiers are not used by the recipes")
+        return path
+    return rspec
+
+
+def read_int_vector_ark(rspec):
+    """Yields (uttid, list[int]) in file order; text or binary Kaldi archives."""
+    path = parse_rspecifier(rspec)
+    with open(path, "rb") as f:
+        data = f.read()
+    pos, n = 0, len(data)
+    while pos < n:
+        while pos < n and data[pos:pos + 1] in b" \n\t\r":
+            pos += 1
+        if pos >= n:
+            break
+        sp = pos
+        while data[sp:sp + 1] not in b" \n\t":
+            sp += 1
+        key = data[pos:sp].decode()
+        pos = sp + 1
+        if data[pos:pos + 2] == b"\0B":                       # binary: \0B \4 <int32 n> (\4 <int32>)*
+            pos += 2
+            assert data[pos] == 4
+            cnt = struct.unpack_from("<i", data, pos + 1)[0]
+            pos += 5
+            vals = []
+            for _ in range(cnt):
+                assert data[pos] == 4
+                vals.append(struct.unpack_from("<i", data, pos + 1)[0])
+                pos += 5
+            yield key, vals
+        else:                                                 # text: rest of the line
+            nl = data.find(b"\n", pos)
+            nl = n if nl < 0 else nl
+            yield key, [int(t) for t in data[pos:nl].split()]
+            pos = nl + 1
+
+
+def read_kaldi_text_matrix(path):
+    """``[ r0c0 r0c1 ...\\n r1c0 ... ]`` -> float64 ndarray (CMVN stats are 2 x (D+1))."""
+    txt = open(path).read()
+    lb, rb = txt.index("["), txt.rindex("]")
+    rows = [r.split() for r in txt[lb + 1:rb].strip().split("\n") if r.strip()]
+    return np.array([[float(v) for v in r] for r in rows], dtype=np.float64)
+
+
+def cmvn_offset_scale(path, splice_width):
+    """(offset, scale) float64 tiled lctx+1+rctx times (trainer/train_transducer_bmuf_otfaug.py:341-355)."""
+    cmvn = read_kaldi_text_matrix(path)
+    mean = cmvn[0][:-1] / cmvn[0][-1]
+    var = cmvn[1][:-1] / cmvn[0][-1] - mean * mean
+    if min(abs(var)) < 1.0e-20:
+        raise ValueError("problematic cmvn_stats, variance too small")
+    return np.tile(-mean, splice_width), np.tile(1.0 / np.sqrt(var), splice_width)
+
+
+def read_lst(data_lst):
+    out = []
+    with open(data_lst, "r", encoding="utf-8") as f:
+        for line in f:
+            p = line.split()
+            if p:
+                out.append((p[0], p[1], p[2]))
+    return out
+
+
+def iter_mrk_seq(mrk_fn, seq_fn):
+    """Yields (uttid, int16 ndarray) -- utils/wav_to_seq.py layout, odd byte counts truncated
+    (loader/otf_utt_loader.py:213-217)."""
+    with open(mrk_fn, "r", encoding="utf-8") as mrk, open(seq_fn, "rb") as seq:
+        for line in mrk:
+            p = line.split()
+            seq.seek(int(p[1]))
+            nb = int(p[2])
+            nb -= nb % 2
+            yield p[0], np.frombuffer(seq.read(nb), dtype="int16")

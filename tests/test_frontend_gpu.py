@@ -89,3 +89,28 @@ def test_bf16_output_and_batch_of_full_length():
     assert frames == [100] * 4 and o32.shape == (4, 100, 240)
     np.testing.assert_allclose(o16, o32, atol=2e-2, rtol=1e-2)
     assert abs(o32.mean(axis=1)).max() < 1e-4            # CMN: zero mean over time
+
+
+def test_loader_feature_mode_matches_oracle(tmp_path):
+    """drop-in loader in the reference's feature-yielding mode: (data [B,T,240] f32 CPU, target, lens, ali_lens)
+    with the features computed by the GPU front end, against the numpy oracle chain on the same draws."""
+    import random
+    from oracle import frontend as ofe
+    from test_loader_cpu import loader_args, make_dataset
+    from pika_b200.loader import otf_utt_loader as L
+    lst, utts = make_dataset(tmp_path, n_utts=4, shards=1)
+    cfg = tmp_path / "fbank.conf"
+    cfg.write_text("--window-type=hamming\n--sample-frequency=16000\n--dither=1\n--low-freq=40\n--high-freq=-200\n--num-mel-bins=80\n")
+    a = loader_args(raw_batches=False, batch_first=True, feat_config=str(cfg))
+    random.seed(3); np.random.seed(3)
+    (data, target, lens, ali_lens), = list(L.dataloader(lst, [], [], a))
+    assert data.dtype == torch.float32 and not data.is_cuda and tuple(data.shape) == (4, int(lens.max()), 240)
+    random.seed(3); np.random.seed(3)
+    for i, (pcm, lab) in enumerate(utts):
+        spr = [0.9, 1.0, 1.1][random.randint(0, 2)]
+        gain = np.random.uniform(-50.0, -10.0)
+        fb = ofe.kaldi_fbank(ofe.augment(pcm, spr, np.float32(gain)).astype(np.float32))
+        ref = ofe.splice(fb, 1, 1)
+        assert int(lens[i]) == ref.shape[0]
+        np.testing.assert_allclose(data[i, :ref.shape[0]].numpy(), ref, atol=1e-2)
+        assert np.abs(data[i, :ref.shape[0]].numpy() - ref).mean() < 5e-4

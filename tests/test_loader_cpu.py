@@ -1,0 +1,117 @@
+"""Host-side loader logic (no GPU): native readers for the recipe's on-disk formats, TU filter, padding,
+end-of-stream protocol and the augmentation draws coming from the reference's RNG streams."""
+import argparse
+import os
+import random
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+
+def make_dataset(tmp_path, n_utts=7, shards=2):
+    rng = np.random.default_rng(0)
+    lines = []
+    utts = []
+    k = 0
+    for s in range(shards):
+        mrk, seq, ark = tmp_path / ("d%d.mrk" % s), tmp_path / ("d%d.seq" % s), tmp_path / ("d%d.ark" % s)
+        off = 0
+        with open(mrk, "w") as fm, open(seq, "wb") as fs, open(ark, "w") as fa:
+            for _ in range(n_utts):
+                n = int(rng.integers(3000, 9000))
+                pcm = rng.integers(-3000, 3000, n).astype(np.int16)
+                lab = rng.integers(1, 50, int(rng.integers(1, 9))).tolist()
+                fs.write(pcm.tobytes())
+                fm.write("utt%03d %d %d\n" % (k, off, n * 2))
+                fa.write("utt%03d %s\n" % (k, " ".join(str(v) for v in lab)))
+                off += n * 2
+                utts.append((pcm, lab))
+                k += 1
+        lines.append("%s %s ark:%s" % (mrk, seq, ark))
+    lst = tmp_path / "data.lst"
+    lst.write_text("\n".join(lines) + "\n")
+    return str(lst), utts
+
+
+def loader_args(**kw):
+    from pika_b200.loader import otf_utt_loader as L
+    p = argparse.ArgumentParser()
+    L.register(p)
+    a = p.parse_args([])
+    a.lctx, a.rctx, a.feats_dim, a.batch_size, a.num_workers, a.padding_tgt = 1, 1, 80, 4, 1, 99
+    a.max_len, a.TU_limit, a.gain_range, a.raw_batches = 1600, 15000, "50,10", True
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def test_register_and_inputdim_match_reference_flags():
+    from pika_b200.loader import otf_utt_loader as L
+    a = loader_args()
+    assert L.get_inputdim(a) == 240
+    for flag in ("lctx", "rctx", "max_len", "num_workers", "sample_rate", "buffer_size", "batch_first", "reverse_labels",
+                 "feat_config", "stride", "batch_size", "SOS", "EOS", "queue_size", "TU_limit", "padding_tgt", "feats_dim",
+                 "snr_range", "gain_range", "speed_rate", "verbose"):
+        assert hasattr(a, flag), flag
+
+
+def test_raw_batches_follow_reference_protocol(tmp_path):
+    from pika_b200.frontend import Frontend
+    from pika_b200.loader import otf_utt_loader as L
+    lst, utts = make_dataset(tmp_path)
+    a = loader_args()
+    random.seed(5); np.random.seed(5)
+    batches = list(L.dataloader(lst, [], [], a))
+    # 14 utterances, batch 4 -> 3 full batches (the trailing partial batch is dropped, as in the reference)
+    assert len(batches) == 3
+    # replay the reference's draw order: per utterance random.randint then np.random.uniform
+    random.seed(5); np.random.seed(5)
+    k = 0
+    for raw, target, lens, ali_lens in batches:
+        B = raw["pcm"].shape[0]
+        assert target.dtype == torch.int32 and lens.dtype == torch.int32
+        for i in range(B):
+            pcm, lab = utts[k]
+            spr = [0.9, 1.0, 1.1][random.randint(0, 2)]
+            gain = np.random.uniform(-50.0, -10.0)
+            n = int(raw["n_samples"][i])
+            assert n == len(pcm) and np.array_equal(raw["pcm"][i, :n].numpy(), pcm)
+            assert abs(float(raw["rate"][i]) - spr) < 1e-7 and abs(float(raw["target_db"][i]) - gain) < 1e-5
+            new_len, frames = Frontend.lengths([n], [spr])
+            assert int(raw["new_len"][i]) == new_len[0] and int(lens[i]) == frames[0]
+            assert target[i, :len(lab)].tolist() == lab and all(v == 99 for v in target[i, len(lab):].tolist())
+            assert int(ali_lens[i]) == len(lab)
+            k += 1
+
+
+def test_tu_filter_and_empty_batch(tmp_path):
+    from pika_b200.loader import otf_utt_loader as L
+    lst, utts = make_dataset(tmp_path, n_utts=4, shards=1)
+    a = loader_args(TU_limit=0)
+    out = list(L.dataloader(lst, [], [], a))
+    assert len(out) == 1 and out[0][0] is None and out[0][2].tolist() == [0] and out[0][3].tolist() == [0]
+    a = loader_args(num_workers=2)
+    lst2, _ = make_dataset(tmp_path, n_utts=4, shards=2)
+    assert len(list(L.dataloader(lst2, [], [], a))) == 2          # one batch per worker, two None sentinels consumed
+
+
+def test_kaldi_readers(tmp_path):
+    from pika_b200.loader import kaldi_io
+    t = tmp_path / "t.ark"
+    t.write_text("a 1 2 3\nb \nc 7\n")
+    assert list(kaldi_io.read_int_vector_ark("ark,t:%s" % t)) == [("a", [1, 2, 3]), ("b", []), ("c", [7])]
+    b = tmp_path / "b.ark"
+    with open(b, "wb") as f:
+        for key, vals in (("k1", [5, 6]), ("k2", [])):
+            f.write(key.encode() + b" \0B\x04" + struct.pack("<i", len(vals)))
+            for v in vals:
+                f.write(b"\x04" + struct.pack("<i", v))
+    assert list(kaldi_io.read_int_vector_ark("ark:%s" % b)) == [("k1", [5, 6]), ("k2", [])]
+    m = tmp_path / "cmvn"
+    m.write_text(" [\n  10 20 5 \n  30 100 0 ]\n")
+    off, sc = kaldi_io.cmvn_offset_scale(str(m), 3)
+    mean, var = np.array([2.0, 4.0]), np.array([30 / 5 - 4.0, 100 / 5 - 16.0])
+    np.testing.assert_allclose(off, np.tile(-mean, 3))
+    np.testing.assert_allclose(sc, np.tile(1 / np.sqrt(var), 3))
