@@ -241,6 +241,17 @@ int pk_lstm_seq_fwd(const float* gx, const void* w_hh_bf16, void* out, int out_d
 int pk_lstm_seq_bwd(const void* dout, int dtype, const float* gates_save, const float* cs, const void* w_hh_bf16, void* dG_bf16,
                     int B, int U, int H, void* ws, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MBR training step helpers (trainer/train_transducer_mbr_bmuf_otfaug.py:197-235): the joint is evaluated only
+ * on the (t,u) nodes of each N-best alignment, so rows are gathered, and the sparse mbr_grad through
+ * log_softmax(sm_scale * out) is formed directly.
+ */
+int pk_gather_rows(const void* src, const int* idx, void* dst, int dtype, long long rows, int C, void* stream);
+int pk_scatter_add_rows(const void* src, const int* idx, float* dst, int dtype, long long rows, int C, void* stream);
+/* dz[r] = scale * coef[r] * (onehot(tok[r]) - softmax(scale * z[r]));  z, dz [rows, ld], first n columns valid */
+int pk_ce_grad(const void* z, int dtype, long long ld, const int* tok, const float* coef, float scale, void* dz,
+               long long rows, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

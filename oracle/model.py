@@ -135,7 +135,7 @@ def prednet_forward(sd, y, blank=0):
     """SOS prepend + embedding + LSTM (trainer/model/transducer.py:90-95).  y [B,U] int64 -> [B,U+1,H]."""
     sos = torch.full((y.shape[0], 1), blank, dtype=torch.long)
     yy = torch.cat((sos, y.long()), 1)
-    emb = F.embedding(yy, sd["embed.weight"])       # padding_idx only affects grads
+    emb = F.embedding(yy, sd["embed.weight"], padding_idx=sd["embed.weight"].shape[0] - 1)   # padding row: no gradient
     return lstm_forward(sd, emb)[0]
 
 

@@ -624,6 +624,57 @@ __global__ void embedding_bwd_kernel(const long long* __restrict__ idx, const T*
     }
 }
 
+
+// =============================================================================== MBR path helpers
+// dst[r, :] = src[idx[r], :]
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, const int* __restrict__ idx, T* __restrict__ dst, long long rows, int C) {
+    const long long r = blockIdx.x;
+    if (r >= rows) return;
+    const T* s = src + (long long)idx[r] * C;
+    for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+        float f[8];
+        V8<T>::load(s + c, f);
+        V8<T>::store(dst + r * C + c, f);
+    }
+}
+// dst[idx[r], :] += src[r, :]   (f32 accumulation)
+template <typename T>
+__global__ void scatter_add_rows_kernel(const T* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst, long long rows, int C) {
+    const long long r = blockIdx.x;
+    if (r >= rows) return;
+    float* d = dst + (long long)idx[r] * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&d[c], to_f32<T>(src[r * C + c]));
+}
+// gradient of sum_r coef[r] * log_softmax(scale * z[r])[tok[r]] w.r.t. z:  scale * coef * (onehot - softmax(scale z))
+template <typename T>
+__global__ void __launch_bounds__(256) ce_grad_kernel(const T* __restrict__ z, long long ld, const int* __restrict__ tok,
+                                                      const float* __restrict__ coef, float scale, T* __restrict__ dz, long long rows, int n) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = warp; r < rows; r += nw) {
+        const T* zr = z + r * ld;
+        T* dr = dz + r * ld;
+        const float cf = coef[r];
+        if (cf == 0.f) {
+            for (int c = lane; c < (int)ld; c += 32) dr[c] = from_f32<T>(0.f);
+            continue;
+        }
+        float m = -INFINITY;
+        for (int c = lane; c < n; c += 32) m = fmaxf(m, to_f32<T>(zr[c]) * scale);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int c = lane; c < n; c += 32) sum += expf(to_f32<T>(zr[c]) * scale - m);
+        const float inv = 1.f / warp_sum(sum);
+        const int y = tok[r];
+        for (int c = lane; c < (int)ld; c += 32) {
+            float g = 0.f;
+            if (c < n) g = scale * cf * ((c == y ? 1.f : 0.f) - expf(to_f32<T>(zr[c]) * scale - m) * inv);
+            dr[c] = from_f32<T>(g);
+        }
+    }
+}
 }  // namespace pk
 
 // ================================================================================================ C ABI
@@ -805,5 +856,23 @@ extern "C" int pk_embedding_bwd(const long long* idx, const void* dout, int dtyp
                                 long long padding_idx, void* stream) {
     const int grid = grid_for(n * E, 256);
     PK_DISPATCH_T(dtype, (embedding_bwd_kernel<T><<<grid, 256, 0, STREAM(stream)>>>(idx, (const T*)dout, ld, E, dtable, n, padding_idx)));
+    DONE();
+}
+
+extern "C" int pk_gather_rows(const void* src, const int* idx, void* dst, int dtype, long long rows, int C, void* stream) {
+    PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
+    PK_DISPATCH_T(dtype, (gather_rows_kernel<T><<<(unsigned)rows, 128, 0, STREAM(stream)>>>((const T*)src, idx, (T*)dst, rows, C)));
+    DONE();
+}
+extern "C" int pk_scatter_add_rows(const void* src, const int* idx, float* dst, int dtype, long long rows, int C, void* stream) {
+    PK_CHECK_ARG(rows > 0, "rows must be > 0");
+    PK_DISPATCH_T(dtype, (scatter_add_rows_kernel<T><<<(unsigned)rows, 256, 0, STREAM(stream)>>>((const T*)src, idx, dst, rows, C)));
+    DONE();
+}
+extern "C" int pk_ce_grad(const void* z, int dtype, long long ld, const int* tok, const float* coef, float scale, void* dz,
+                          long long rows, int n, void* stream) {
+    PK_CHECK_ARG(rows > 0 && n > 0 && ld >= n, "bad shape");
+    const int grid = grid_for(rows, 8);
+    PK_DISPATCH_T(dtype, (ce_grad_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)z, ld, tok, coef, scale, (T*)dz, rows, n)));
     DONE();
 }

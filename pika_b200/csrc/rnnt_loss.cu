@@ -15,6 +15,8 @@
 //                           dlogits = -softmax * (gb + gl) + [v==blank] gb + [v==label] gl
 //                           (in place if dlogits aliases logits).
 // Algorithmic HBM traffic: 3 * B*T*(U+1)*V * sizeof(elem)  (+ O(nodes) fp32).
+#include <cstdlib>
+
 #include "../../include/pika_b200.h"
 #include "common.cuh"
 
@@ -295,9 +297,8 @@ __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
 // gradient) accumulate in registers for free.  GRAD_RU rows are in flight per thread.
 constexpr int GRAD_THREADS = 256;
 constexpr int GRAD_MAXG = 4;
-constexpr int GRAD_RU = 2;
-template <typename T>
-__global__ void __launch_bounds__(GRAD_THREADS, 3) rnnt_grad_kernel(const T* logits, const int* __restrict__ labels,
+template <typename T, int GRAD_RU, int MINB>
+__global__ void __launch_bounds__(GRAD_THREADS, MINB) rnnt_grad_kernel(const T* logits, const int* __restrict__ labels,
                                                                     const int* __restrict__ label_lens, RnntDims d,
                                                                     const float* __restrict__ lse_in, const float* __restrict__ gb_in,
                                                                     const float* __restrict__ gl_in, T* dlogits, float* __restrict__ colsum,
@@ -449,19 +450,28 @@ extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* la
     if (dlogits != nullptr) {
         PK_CHECK_ARG(ldv / vn <= GRAD_THREADS * GRAD_MAXG, "V too large for the gradient kernel (V <= 8192 bf16 / 4096 f32)");
         if (dlogits_colsum) PK_CHECK_CUDA(cudaMemsetAsync(dlogits_colsum, 0, sizeof(float) * ldv, stream));
-        const int gcta = num_sms() * 12;
+        static int variant = -1;                         // tuning hook (PK_RNNT_GRAD_VARIANT=0..3), default chosen by measurement
+        if (variant < 0) { const char* e = getenv("PK_RNNT_GRAD_VARIANT"); variant = e ? atoi(e) : 1; }
+        const int ru = (variant == 0) ? 1 : (variant == 3 ? 4 : 2);
+        const int ctas_per_sm = (variant == 2) ? 2 : 3;
+        const int gcta = num_sms() * ctas_per_sm * 4;
         long long rpc = (rows + gcta - 1) / gcta;
-        rpc = (rpc + GRAD_RU - 1) / GRAD_RU * GRAD_RU;
+        rpc = (rpc + ru - 1) / ru * ru;
         if (rpc > 2048) rpc = 2048;                      // 16 bytes of shared memory per row
         const int ggrid = (int)((rows + rpc - 1) / rpc);
         const size_t gsmem = (size_t)rpc * 16;
-        if (dtype == PK_BF16)
-            rnnt_grad_kernel<__nv_bfloat16><<<ggrid, GRAD_THREADS, gsmem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), labels,
-                                                                              label_lens, d, lse, gb, gl,
-                                                                              reinterpret_cast<__nv_bfloat16*>(dlogits), dlogits_colsum, rpc);
-        else
-            rnnt_grad_kernel<float><<<ggrid, GRAD_THREADS, gsmem, stream>>>(reinterpret_cast<const float*>(logits), labels, label_lens, d,
-                                                                       lse, gb, gl, reinterpret_cast<float*>(dlogits), dlogits_colsum, rpc);
+#define PK_GRAD_LAUNCH(TT, RU, MB)                                                                                         \
+        rnnt_grad_kernel<TT, RU, MB><<<ggrid, GRAD_THREADS, gsmem, stream>>>(reinterpret_cast<const TT*>(logits), labels, label_lens, d, lse, \
+                                                                            gb, gl, reinterpret_cast<TT*>(dlogits), dlogits_colsum, rpc)
+        if (dtype == PK_BF16) {
+            if (variant == 0) PK_GRAD_LAUNCH(__nv_bfloat16, 1, 3);
+            else if (variant == 2) PK_GRAD_LAUNCH(__nv_bfloat16, 2, 2);
+            else if (variant == 3) PK_GRAD_LAUNCH(__nv_bfloat16, 4, 2);
+            else PK_GRAD_LAUNCH(__nv_bfloat16, 2, 3);
+        } else {
+            PK_GRAD_LAUNCH(float, 2, 2);
+        }
+#undef PK_GRAD_LAUNCH
         PK_CHECK_LAUNCH(); count_launch();
     }
     return 0;

@@ -277,3 +277,19 @@ def lstm_seq_bwd(dout, gates_save, cs, w_hh, dG):
     assert dout.is_contiguous() and dG.dtype == torch.bfloat16 and dG.is_contiguous()
     check(lib.pk_lstm_seq_bwd(_P(dout), _I(_dt(dout)), _P(gates_save), _P(cs), _P(w_hh), _P(dG), _I(B), _I(U), _I(H),
                               _P(_lstm_scratch(H, dout.device)), _stream()), "pk_lstm_seq_bwd")
+
+
+def gather_rows(src, idx, dst):
+    rows, C = dst.shape
+    check(lib.pk_gather_rows(_P(src), _P(idx), _P(dst), _I(_dt(src)), _L(rows), _I(C), _stream()), "pk_gather_rows")
+
+
+def scatter_add_rows(src, idx, dst):
+    rows, C = src.shape
+    assert dst.dtype == torch.float32
+    check(lib.pk_scatter_add_rows(_P(src), _P(idx), _P(dst), _I(_dt(src)), _L(rows), _I(C), _stream()), "pk_scatter_add_rows")
+
+
+def ce_grad(z, tok, coef, scale, dz, n):
+    rows, ld = z.shape
+    check(lib.pk_ce_grad(_P(z), _I(_dt(z)), _L(ld), _P(tok), _P(coef), _F(scale), _P(dz), _L(rows), _I(n), _stream()), "pk_ce_grad")

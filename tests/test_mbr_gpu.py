@@ -1,0 +1,75 @@
+"""MBR training batch (BASELINE config 4 path, small shapes): every parameter gradient of
+pika_b200.trainer.mbr.mbr_forward_backward against the torch-CPU restatement of
+trainer/train_transducer_mbr_bmuf_otfaug.py:140-235 (oracle/mbr.py) on the SAME N-best list, which itself comes
+from the batched device beam search.  fp32-class mode, dropout off, BatchNorm in train mode."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def test_mbr_step_matches_oracle(golden_dir):
+    from fixture_utils import decode_fixture_reinit
+    from oracle import mbr as ombr
+    from pika_b200 import engine
+    from pika_b200.decoder.beam_transducer import GlobalScorer
+    from pika_b200.decoder.transducer_decoder import TransducerDecoder
+    from pika_b200.model.transducer import Net
+    from pika_b200.trainer.mbr import mbr_forward_backward
+    V, beam = 40, 4
+    torch.manual_seed(777)
+    margs = types.SimpleNamespace(rnn_size=1024, local_rank=0, decoder_type="rnn", brnn=True, encoder_type="transformer",
+                                  embd_dim=100, padding_idx=V, dropout=0.2, dec_layers=2, enc_layers=9)
+    m = Net(margs, 240, V)
+    decode_fixture_reinit(m)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    for k, _ in m.named_parameters():
+        sd[k].requires_grad_(True)
+    m = m.cuda()
+    d = np.load(os.path.join(golden_dir, "decode_small.npz"))
+    x = torch.from_numpy(d["x"])
+    tl = torch.from_numpy(d["tlens"]).int()
+    g = torch.Generator().manual_seed(11)
+    ul = torch.tensor([5, 3, 4], dtype=torch.int32)
+    target = torch.full((3, 5), V, dtype=torch.long)
+    for i in range(3):
+        target[i, :ul[i]] = torch.randint(1, V, (int(ul[i]),), generator=g)
+    engine.set_precision("fp32")
+    engine.set_dropout_enabled(False)
+    try:
+        m.eval()
+        dargs = types.SimpleNamespace(las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None, nonblk_reward=0.0)
+        dec = TransducerDecoder(m, 3, beam, n_best=beam, blk=0, global_scorer=GlobalScorer(), sm_scale=0.8, cuda=True,
+                                beam_prune=False, args=dargs)
+        ret, _ = dec.decode_batch(x.cuda(), tl, max_len=[int(t) + int(u) + 3 for t, u in zip(tl, ul)])
+        m.train()
+        for p in m.parameters():
+            p.grad = None
+        mbr_loss, rnnt_costs = mbr_forward_backward(m, x.cuda(), target.cuda(), tl.cuda(), ul.cuda(), ret, blk=0, rnnt_scale=0.5,
+                                                    sm_scale=0.8)
+        hyps = [[[int(t) for t in h] for h in row] for row in ret["predictions"]]
+        scores = [[float(s) for s in row] for row in ret["scores"]]
+        mbr_ref, costs_ref = ombr.mbr_loss_and_grads(sd, x, target, tl.numpy(), ul.numpy(), hyps, scores, 0, V, 0.5, 0.8)
+        assert abs(mbr_loss - mbr_ref) < 1e-4 * max(1.0, abs(mbr_ref))
+        np.testing.assert_allclose(rnnt_costs.cpu().numpy(), costs_ref * 0.5, rtol=1e-3)
+        bad = []
+        for k, p in m.named_parameters():
+            ref = sd[k].grad
+            if ref is None or ref.norm() < 1e-7:
+                continue
+            r = rel(p.grad, ref)
+            if r > 5e-3:
+                bad.append((k, r, float(ref.norm())))
+        assert not bad, bad
+    finally:
+        engine.set_precision("bf16")
+        engine.set_dropout_enabled(True)
