@@ -36,6 +36,12 @@ template <> struct Vec16<__nv_bfloat16> {
     PK_DEVICE static uint4 pack(const float (&f)[8]) {
         return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     }
+    PK_DEVICE static float vmax(const uint4& q) {         // packed bf16x2 max: 3 + 1 instructions for 8 elements
+        const __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.x), *reinterpret_cast<const __nv_bfloat162*>(&q.y));
+        const __nv_bfloat162 b = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.z), *reinterpret_cast<const __nv_bfloat162*>(&q.w));
+        const __nv_bfloat162 c = __hmax2(a, b);
+        return fmaxf(__low2float(c), __high2float(c));
+    }
 };
 template <> struct Vec16<float> {
     static constexpr int N = 4;
@@ -44,6 +50,9 @@ template <> struct Vec16<float> {
     }
     PK_DEVICE static uint4 pack(const float (&f)[4]) {
         return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+    PK_DEVICE static float vmax(const uint4& q) {
+        return fmaxf(fmaxf(__uint_as_float(q.x), __uint_as_float(q.y)), fmaxf(__uint_as_float(q.z), __uint_as_float(q.w)));
     }
 };
 
@@ -88,29 +97,32 @@ __global__ void __launch_bounds__(256) rnnt_rowstats_kernel(const T* __restrict_
         const T* rp = logits + row * (long long)d.ldv;
         const uint4* vp = reinterpret_cast<const uint4*>(rp);
         float m = -INFINITY, s = 0.f;          // running max (in log2 units) and sum of 2^(x*log2e - m)
-        for (int i0 = lane; i0 < nvec; i0 += 32 * ROWSTATS_UNROLL) {
+        const int nfull = d.V / VN;            // vectors without a tail; the (rare) partial vector is handled after the loop
+        for (int i0 = lane; i0 < nfull; i0 += 32 * ROWSTATS_UNROLL) {
             uint4 q[ROWSTATS_UNROLL];
 #pragma unroll
             for (int k = 0; k < ROWSTATS_UNROLL; ++k) {
                 const int i = i0 + k * 32;
-                if (i < nvec) q[k] = ld_stream(vp + i);
+                if (i < nfull) q[k] = ld_stream(vp + i);
             }
 #pragma unroll
             for (int k = 0; k < ROWSTATS_UNROLL; ++k) {
                 const int i = i0 + k * 32;
-                if (i < nvec) {
+                if (i < nfull) {
+                    const float cm = Vec16<T>::vmax(q[k]) * kLog2e;
+                    if (cm > m) { s *= exp2f(m - cm); m = cm; }   // rare after the first chunks
                     float f[VN];
                     Vec16<T>::unpack(q[k], f);
-                    float cm = -INFINITY;
 #pragma unroll
-                    for (int e = 0; e < VN; ++e) {
-                        f[e] = (i * VN + e < d.V) ? f[e] * kLog2e : -INFINITY;
-                        cm = fmaxf(cm, f[e]);
-                    }
-                    if (cm > m) { s *= exp2f(m - cm); m = cm; }   // rare after the first chunks
-#pragma unroll
-                    for (int e = 0; e < VN; ++e) s += exp2f(f[e] - m);
+                    for (int e = 0; e < VN; ++e) s += exp2f(fmaf(f[e], kLog2e, -m));
                 }
+            }
+        }
+        if (nfull * VN < d.V && lane == 0) {   // partial last vector (V not a multiple of 16 bytes)
+            for (int v = nfull * VN; v < d.V; ++v) {
+                const float x = to_f32<T>(rp[v]) * kLog2e;
+                if (x > m) { s *= exp2f(m - x); m = x; }
+                s += exp2f(x - m);
             }
         }
         // combine the 32 lane-local (m, s) pairs
@@ -367,12 +379,16 @@ __global__ void __launch_bounds__(GRAD_THREADS, MINB) rnnt_grad_kernel(const T* 
                     float f[VN];
                     Vec16<T>::unpack(q[k][gq], f);
 #pragma unroll
-                    for (int e = 0; e < VN; ++e) {
-                        const int v = i * VN + e;
-                        float gv = exp2f(f[e] * kLog2e - l2) * gsum;
-                        if (v == 0) gv += gb;
-                        if (v == y) gv += gl;
-                        f[e] = (v < d.V) ? gv : 0.f;
+                    for (int e = 0; e < VN; ++e) f[e] = exp2f(fmaf(f[e], kLog2e, -l2)) * gsum;
+                    const int v0 = i * VN;
+                    if (v0 == 0) f[0] += gb;                                   // blank column
+                    if (y >= v0 && y < v0 + VN) {                              // label column (one thread per row)
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) if (v0 + e == y) f[e] += gl;
+                    }
+                    if (v0 + VN > d.V) {                                       // row padding [V, ldv)
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) if (v0 + e >= d.V) f[e] = 0.f;
                     }
                     const uint4 packed = Vec16<T>::pack(f);
                     st_stream(op + i, packed);
