@@ -324,12 +324,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 // S f32 [rows, ld_s] (first n valid) -> P (T) [rows, ld_p] and Pd = dropout(P); pad columns [n, ld_p) zeroed.
 // One warp per row; the row lives in registers (lane l owns columns [l*8 + k*256, +8), k < 4, n <= 1024) and every
 // access is a 16/32-byte vector, so S is read exactly once.  ld_s, ld_p multiples of 8.
-constexpr int SM_CH = 4;
 PK_DEVICE void ld8f(const float* p, float (&f)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
-template <typename T>
+template <typename T, int SM_CH>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, long long ld_s, T* __restrict__ P,
                                                           T* __restrict__ Pd, long long ld_p, long long rows, int n,
                                                           uint32_t drop_thresh, float drop_scale, uint32_t seed) {
@@ -375,7 +374,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
     }
 }
 // dS[r,c] = P * (dP' - sum_c dP'*P), dP' = dPd * mask * scale; written as T with pad zeroed.
-template <typename T>
+template <typename T, int SM_CH>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ dPd, long long ld_d, const T* __restrict__ P,
                                                           long long ld_p, T* __restrict__ dS, long long rows, int n,
                                                           uint32_t drop_thresh, float drop_scale, uint32_t seed) {
@@ -779,11 +778,12 @@ extern "C" int pk_layernorm_bwd(const void* dy, const void* x, void* dx, int dty
 
 extern "C" int pk_softmax_fwd(const float* S, long long ld_s, void* P, void* Pd, int dtype, long long ld_p, long long rows, int n,
                               float drop_p, uint32_t seed, void* stream) {
-    PK_CHECK_ARG(rows > 0 && n > 0 && ld_p >= n && ld_s >= ld_p && ld_p <= 1024 && ld_p % 8 == 0 && ld_s % 8 == 0, "softmax rows: ld % 8 == 0, <= 1024 wide");
+    PK_CHECK_ARG(rows > 0 && n > 0 && ld_p >= n && ld_s >= ld_p && ld_p <= 2048 && ld_p % 8 == 0 && ld_s % 8 == 0, "softmax rows: ld % 8 == 0, <= 2048 wide");
     const int grid = grid_for(rows, 8);
     const uint32_t th = drop_thresh_of(drop_p);
     const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed)));
+    if (ld_p <= 1024) { PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T, 4><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed))); }
+    else { PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T, 8><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed))); }
     DONE();
 }
 extern "C" int pk_softmax_bwd(const float* dPd, long long ld_d, const void* P, long long ld_p, void* dS, int dtype, long long rows,
@@ -791,7 +791,9 @@ extern "C" int pk_softmax_bwd(const float* dPd, long long ld_d, const void* P, l
     const int grid = grid_for(rows, 8);
     const uint32_t th = drop_thresh_of(drop_p);
     const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    PK_DISPATCH_T(dtype, (softmax_bwd_kernel<T><<<grid, 256, 0, STREAM(stream)>>>(dPd, ld_d, (const T*)P, ld_p, (T*)dS, rows, n, th, sc, seed)));
+    PK_CHECK_ARG(ld_p <= 2048 && ld_p % 8 == 0 && ld_d % 8 == 0, "softmax rows: ld % 8 == 0, <= 2048 wide");
+    if (ld_p <= 1024) { PK_DISPATCH_T(dtype, (softmax_bwd_kernel<T, 4><<<grid, 256, 0, STREAM(stream)>>>(dPd, ld_d, (const T*)P, ld_p, (T*)dS, rows, n, th, sc, seed))); }
+    else { PK_DISPATCH_T(dtype, (softmax_bwd_kernel<T, 8><<<grid, 256, 0, STREAM(stream)>>>(dPd, ld_d, (const T*)P, ld_p, (T*)dS, rows, n, th, sc, seed))); }
     DONE();
 }
 
