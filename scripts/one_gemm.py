@@ -1,13 +1,16 @@
-"""One GEMM shape, a few launches (for ncu captures)."""
+"""One GEMM shape, a few launches (for ncu captures).  usage: one_gemm.py M N K [f32|bf16] [a_mn] [b_mn]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pika_b200 import kernels as K
-M, N, Kd = [int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (32000, 4096, 1024))]
-cdt = torch.float32 if (len(sys.argv) > 4 and sys.argv[4] == "f32") else torch.bfloat16
-a = torch.randn(M, Kd, device="cuda").to(torch.bfloat16)
-b = torch.randn(N, Kd, device="cuda").to(torch.bfloat16)
-c = torch.empty(M, N, device="cuda", dtype=cdt)
+a = sys.argv[1:]
+M, N, Kd = [int(v) for v in (a[0:3] if len(a) > 2 else (32000, 4096, 1024))]
+cdt = torch.float32 if (len(a) > 3 and a[3] == "f32") else torch.bfloat16
+a_mn = len(a) > 4 and a[4] == "1"
+b_mn = len(a) > 5 and a[5] == "1"
+A = torch.randn((Kd, M) if a_mn else (M, Kd), device="cuda").to(torch.bfloat16)
+B = torch.randn((Kd, N) if b_mn else (N, Kd), device="cuda").to(torch.bfloat16)
+C = torch.empty(M, N, device="cuda", dtype=cdt)
 for _ in range(4):
-    K.gemm(a, b, c)
+    K.gemm(A, B, C, a_mn=a_mn, b_mn=b_mn, k_splits=1)
 torch.cuda.synchronize()
