@@ -13,6 +13,7 @@
 // loop (kz) for per-utterance wgrad.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/pika_b200.h"
@@ -461,14 +462,24 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
     int splits = 1;
     const bool plain_epi = d->bias == nullptr && d->act == PK_ACT_NONE && d->drop_p == 0.f && gp.aux_mode == PK_AUX_NONE;
     if (d->k_splits > 0) splits = d->k_splits;
-    else if (gp.c_is_f32 && plain_epi && gp.zb0 == 1 && gp.zb1 == 1 && out_tiles < 6 * num_sms() && k_iters_total >= 16) {
-        // pick the split count (<= 16, >= 8 k-iterations each) that wastes the fewest SM-slots in the last wave
+    else if (gp.c_is_f32 && plain_epi && gp.zb0 == 1 && gp.zb1 == 1 && k_iters_total >= 16) {
+        static int mode = -1;                            // tuning hook: PK_GEMM_SPLIT_MODE=0 (fill two waves) | 1 (least last-wave waste)
+        if (mode < 0) { const char* e = getenv("PK_GEMM_SPLIT_MODE"); mode = e ? atoi(e) : 0; }   // measured: mode 0 = 91.2 ms/step, mode 1 = 94-97 (profiles/r01_notes.md)
         const int sms = num_sms();
-        double best = 0.0;
-        for (int s = 1; s <= 16 && s <= k_iters_total / 8; ++s) {
-            const long long units = out_tiles * s;
-            const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
-            if (eff > best + 0.02) { best = eff; splits = s; }
+        if (mode == 0) {
+            if (out_tiles < 2 * sms) {
+                splits = (int)((2 * sms + out_tiles / 2) / out_tiles);
+                if (splits > k_iters_total / 8) splits = k_iters_total / 8;
+                if (splits > 64) splits = 64;
+            }
+        } else if (out_tiles < 6 * sms) {
+            // pick the split count (<= 16, >= 8 k-iterations each) that wastes the fewest SM-slots in the last wave
+            double best = 0.0;
+            for (int s = 1; s <= 16 && s <= k_iters_total / 8; ++s) {
+                const long long units = out_tiles * s;
+                const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
+                if (eff > best + 0.02) { best = eff; splits = s; }
+            }
         }
         if (splits < 1) splits = 1;
     }

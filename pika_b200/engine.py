@@ -658,6 +658,8 @@ def encoder_forward_act(enc, x):
     training = enc.training
     B, T, D = x.shape
     C = enc.tdnn_nhid
+    if T < 43:
+        raise ValueError("encoder input has %d frames; the TDNN stack needs at least 43 (receptive field 21+1+21)" % T)
     h = linear(_to_act(x).view(B * T, D), enc.fc_in.weight, enc.fc_in.bias, act=True)
     h = BatchNormFn.apply(h, enc.bn_in, training, enc.bn_in.weight, enc.bn_in.bias)
     for l, (conv, bn) in enumerate(zip(enc.hidden_conv, enc.hidden_bn)):

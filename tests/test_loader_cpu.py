@@ -10,7 +10,7 @@ import pytest
 import torch
 
 
-def make_dataset(tmp_path, n_utts=7, shards=2):
+def make_dataset(tmp_path, n_utts=7, shards=2, n_lo=3000, n_hi=9000):
     rng = np.random.default_rng(0)
     lines = []
     utts = []
@@ -20,7 +20,7 @@ def make_dataset(tmp_path, n_utts=7, shards=2):
         off = 0
         with open(mrk, "w") as fm, open(seq, "wb") as fs, open(ark, "w") as fa:
             for _ in range(n_utts):
-                n = int(rng.integers(3000, 9000))
+                n = int(rng.integers(n_lo, n_hi))
                 pcm = rng.integers(-3000, 3000, n).astype(np.int16)
                 lab = rng.integers(1, 50, int(rng.integers(1, 9))).tolist()
                 fs.write(pcm.tobytes())

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def test_train_cli_two_epochs(tmp_path):
     from test_loader_cpu import make_dataset
     from pika_b200.trainer import train_transducer_bmuf_otfaug as T
-    lst, utts = make_dataset(tmp_path, n_utts=8, shards=1)
+    lst, utts = make_dataset(tmp_path, n_utts=8, shards=1, n_lo=14000, n_hi=22000)
     cfg = tmp_path / "fbank.conf"
     cfg.write_text("--window-type=hamming\n--sample-frequency=16000\n--dither=1\n--low-freq=40\n--high-freq=-200\n--num-mel-bins=80\n")
     cmvn = tmp_path / "cmvn.stats"
