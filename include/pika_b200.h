@@ -87,6 +87,7 @@ typedef struct {
     float aux_scale;
     int block_n;                      /* 0 = auto; else 64 | 128 | 256 */
     int k_splits;                     /* 0 = auto; 1 = off; >1 = split the reduction (plain f32 2-D C only) */
+    int two_sm;                       /* 0 = auto (CTA-pair kernel for 256-wide tiles when M > 128); 1 = force; -1 = never */
 } pk_gemm_desc;
 
 int pk_gemm_bf16(const pk_gemm_desc* desc, void* stream);

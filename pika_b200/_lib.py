@@ -49,6 +49,7 @@ class GemmDesc(ctypes.Structure):
         ("aux_scale", ctypes.c_float),
         ("block_n", ctypes.c_int),
         ("k_splits", ctypes.c_int),
+        ("two_sm", ctypes.c_int),
     ]
 
 

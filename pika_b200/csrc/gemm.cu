@@ -313,6 +313,276 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ CTA-pair variant
+// cta_group::2: two CTAs on one TPC cooperate on a 256 x 256 tile.  Each CTA stages its own 128 rows of A and
+// HALF of B (128 of the 256 N-rows), so shared-memory and L2->SM traffic per CTA drop by a third and the ring
+// deepens from 4 to 6 stages; the leader CTA's single thread issues tcgen05.mma.cta_group::2 for both, the
+// accumulator rows of each CTA live in its own TMEM, and each CTA runs its own epilogue.
+struct Gemm2Cfg {
+    static constexpr int BN = 256;
+    static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;          // this CTA's half of B
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = 6;
+    static constexpr int C_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BIAS_OFF = C_OFF + 2 * C_STAGE_BYTES;
+    static constexpr int BAR_OFF = BIAS_OFF + BN * 4;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <bool A_MN, bool B_MN, bool CF32>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_2sm_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = Gemm2Cfg;
+    constexpr int BN = Cfg::BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* bias_smem = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < p.n_pairs; ++i) {
+            tma_prefetch_desc(&p.a[i]);
+            tma_prefetch_desc(&p.b[i]);
+        }
+        tma_prefetch_desc(&p.c);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 2);              // leader's expect_tx arrive + the peer producer's remote arrive
+            mbar_init(&empty_bar[s], 1);             // tcgen05.commit multicast
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);             // tcgen05.commit multicast
+            mbar_init(&tmem_empty[a], 8);            // 4 epilogue warps x 2 CTAs (used in the leader only)
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_m2 = (p.M + 255) / 256;
+    const int tiles_per_z = tiles_m2 * p.tiles_n;
+    const int num_tiles = tiles_per_z * p.zb0 * p.zb1 * p.k_splits;
+    const int k_iters_total = p.n_pairs * p.kz_count * p.num_k_blocks;
+    const int kzb = p.kz_count * p.num_k_blocks;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = pair; unit < num_tiles; unit += num_pairs) {
+                const int tile = unit / p.k_splits, split = unit - tile * p.k_splits;
+                const int z = tile / tiles_per_z;
+                const int r = tile - z * tiles_per_z;
+                const int mb = r / p.tiles_n, nb = r - mb * p.tiles_n;
+                const int zb1 = z / p.zb0, zb0 = z - zb1 * p.zb0;
+                const int m0 = mb * 256 + (int)rank * BM, n0 = nb * BN + (int)rank * (BN / 2);
+                const int i0 = split * p.iters_per_split, i1 = min(k_iters_total, i0 + p.iters_per_split);
+                for (int i = i0; i < i1; ++i) {
+                    const int pr = i / kzb;
+                    const int rem = i - pr * kzb;
+                    const int kz = rem / p.num_k_blocks, kb = rem - kz * p.num_k_blocks;
+                    const int a2 = pick_sel(p.a_sel2, zb0, zb1, kz), a3 = pick_sel(p.a_sel3, zb0, zb1, kz);
+                    const int b2 = pick_sel(p.b_sel2, zb0, zb1, kz), b3 = pick_sel(p.b_sel3, zb0, zb1, kz);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    if (A_MN) {
+#pragma unroll
+                        for (int c = 0; c < BM / 64; ++c)
+                            tma_load_4d_2sm(sa + c * (64 * BK * 2), &p.a[pr], &full_bar[stage], m0 + c * 64, kb * BK + p.a_off[pr], a2, a3);
+                    } else {
+                        tma_load_4d_2sm(sa, &p.a[pr], &full_bar[stage], kb * BK, m0 + p.a_off[pr], a2, a3);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int c = 0; c < BN / 128; ++c)
+                            tma_load_4d_2sm(sb + c * (64 * BK * 2), &p.b[pr], &full_bar[stage], n0 + c * 64, kb * BK + p.b_off[pr], b2, b3);
+                    } else {
+                        tma_load_4d_2sm(sb, &p.b[pr], &full_bar[stage], kb * BK, n0 + p.b_off[pr], b2, b3);
+                    }
+                    if (rank != 0) mbar_arrive_remote(&full_bar[stage], 0);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int unit = pair; unit < num_tiles; unit += num_pairs, ++it) {
+                const int split = unit % p.k_splits;
+                const int k_iters = min(k_iters_total, (split + 1) * p.iters_per_split) - split * p.iters_per_split;
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int k = 0; k < k_iters; ++k) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < BK / 16; ++k4) {
+                        const uint64_t ad = A_MN ? make_smem_desc_sw128(sa + k4 * 2048, 64 * BK * 2, 1024)
+                                                 : make_smem_desc_sw128(sa + k4 * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? make_smem_desc_sw128(sb + k4 * 2048, 64 * BK * 2, 1024)
+                                                 : make_smem_desc_sw128(sb + k4 * 32, 16, 1024);
+                        umma_bf16_2sm(d_tmem, ad, bd, idesc, (k > 0 || k4 > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&empty_bar[stage], 3);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tmem_full[acc], 3);
+            }
+        }
+    } else {
+        // ===================================================== epilogue (warps 2..5)
+        // Compact loop over 16-byte output groups (8 bf16 / 4 f32 columns): one small tcgen05.ld per
+        // group keeps the body a few dozen instructions, so it stays resident in the instruction cache.
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // tile row owned by this thread
+        const int et = threadIdx.x - 64;        // 0..127
+        const bool store_thread = (et == 0);
+        constexpr int GW = CF32 ? 4 : 8;        // columns per 16-byte group
+        constexpr int CH = 8 * GW;              // columns per 128-byte staging row
+        uint8_t* cst = smem + Cfg::C_OFF;
+        const float relu_floor = (p.act == PK_ACT_RELU) ? 0.f : -INFINITY;
+        if (p.bias == nullptr) {
+            for (int j = et; j < BN; j += 128) bias_smem[j] = 0.f;
+            named_bar_sync(2, 128);
+        }
+        int it = 0;
+        uint32_t chunk_ctr = 0;
+        for (int unit = pair; unit < num_tiles; unit += num_pairs, ++it) {
+            const int tile = unit / p.k_splits;
+            const int z = tile / tiles_per_z;
+            const int r = tile - z * tiles_per_z;
+            const int mb = r / p.tiles_n, nb = r - mb * p.tiles_n;
+            const int zb1 = z / p.zb0, zb0 = z - zb1 * p.zb0;
+            const int m0 = mb * 256 + (int)rank * BM, n0 = nb * BN;
+            const int acc = it & 1;
+            const int m = m0 + row;
+            if (p.bias != nullptr) {
+                named_bar_sync(2, 128);         // previous tile's readers are done with bias_smem
+                for (int j = et; j < BN; j += 128) bias_smem[j] = (n0 + j < p.N) ? p.bias[n0 + j] : 0.f;
+                named_bar_sync(2, 128);
+            }
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            const bool row_ok = m < p.M;
+            const unsigned char* aux_row = nullptr;
+            if (p.aux_mode != PK_AUX_NONE && row_ok) {
+                const long long off = (long long)m * p.aux_sm + (long long)zb0 * p.aux_s0 + (long long)zb1 * p.aux_s1;
+                aux_row = reinterpret_cast<const unsigned char*>(p.aux) + off * (p.aux_is_f32 ? 4 : 2);
+            }
+            const uint64_t lin_row = ((uint64_t)(zb1 * p.zb0 + zb0) * (uint64_t)p.M + (uint64_t)m) * (uint64_t)p.N;
+            constexpr int n_chunks = BN / CH;
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const int nc0 = n0 + ch * CH;
+                if (nc0 >= p.N) break;           // uniform across the 4 epilogue warps
+                uint8_t* sbuf = cst + (chunk_ctr & 1) * C_STAGE_BYTES;
+                if (store_thread) tma_store_wait_read<1>();     // the buffer used two chunks ago is free
+                named_bar_sync(1, 128);
+                uint8_t* srow = sbuf + row * 128;
+#pragma unroll 2
+                for (int gq = 0; gq < 8; ++gq) {
+                    uint32_t rr[GW];
+                    if (CF32) tmem_ld_32x4(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[4]>(&rr[0]));
+                    else tmem_ld_32x8(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[8]>(&rr[0]));
+                    tmem_ld_wait();
+                    const int ncol = nc0 + gq * GW;
+                    float x[GW];
+                    const float* bsm = bias_smem + ch * CH + gq * GW;
+#pragma unroll
+                    for (int e = 0; e < GW; ++e) x[e] = fmaxf(fmaf(__uint_as_float(rr[e]), p.alpha, bsm[e]), relu_floor);
+                    if (p.drop_thresh != 0u) {
+#pragma unroll
+                        for (int e = 0; e < GW; ++e)
+                            x[e] = drop_keep(lin_row + (uint64_t)(ncol + e), p.drop_seed, p.drop_thresh) ? x[e] * p.drop_scale : 0.f;
+                    }
+                    if (aux_row != nullptr && ncol < p.N) {       // N % GW == 0 is enforced on the host when aux is used
+                        float a[GW];
+                        if (p.aux_is_f32) {
+                            const float4* ap = reinterpret_cast<const float4*>(aux_row + (size_t)ncol * 4);
+#pragma unroll
+                            for (int e4 = 0; e4 < GW / 4; ++e4) {
+                                const float4 t4 = ap[e4];
+                                a[e4 * 4 + 0] = t4.x; a[e4 * 4 + 1] = t4.y; a[e4 * 4 + 2] = t4.z; a[e4 * 4 + 3] = t4.w;
+                            }
+                        } else {
+                            if (GW == 8) {
+                                const uint4 t4 = *reinterpret_cast<const uint4*>(aux_row + (size_t)ncol * 2);
+                                a[0] = bf16lo(t4.x); a[1] = bf16hi(t4.x); a[2] = bf16lo(t4.y); a[3] = bf16hi(t4.y);
+                                a[GW - 4] = bf16lo(t4.z); a[GW - 3] = bf16hi(t4.z); a[GW - 2] = bf16lo(t4.w); a[GW - 1] = bf16hi(t4.w);
+                            } else {
+                                const uint2 t2 = *reinterpret_cast<const uint2*>(aux_row + (size_t)ncol * 2);
+                                a[0] = bf16lo(t2.x); a[1] = bf16hi(t2.x); a[2] = bf16lo(t2.y); a[3] = bf16hi(t2.y);
+                            }
+                        }
+                        if (p.aux_mode == PK_AUX_ADD) {
+#pragma unroll
+                            for (int e = 0; e < GW; ++e) x[e] += a[e];
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < GW; ++e) x[e] = (a[e] != 0.f) ? x[e] * p.aux_scale : 0.f;
+                        }
+                    }
+                    uint4 w;
+                    if (CF32) {
+                        w = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+                    } else {
+                        w.x = pack_bf16x2(x[0], x[1]); w.y = pack_bf16x2(x[2], x[3]);
+                        w.z = pack_bf16x2(x[GW - 4], x[GW - 3]); w.w = pack_bf16x2(x[GW - 2], x[GW - 1]);
+                    }
+                    *reinterpret_cast<uint4*>(srow + ((gq ^ (row & 7)) << 4)) = w;
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (store_thread) {
+                    if (p.c_accumulate) tma_reduce_add_4d(&p.c, sbuf, nc0, m0, zb0, zb1);
+                    else tma_store_4d(&p.c, sbuf, nc0, m0, zb0, zb1);
+                    tma_store_commit();
+                }
+                ++chunk_ctr;
+            }
+            // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (rank == 0) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_remote(&tmem_empty[acc], 0); }
+        }
+        if (store_thread) tma_store_wait<0>();
+    }
+
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -377,6 +647,37 @@ static int launch_gemm(const GemmParams& gp, int grid, cudaStream_t stream) {
     return 0;
 }
 
+template <bool A_MN, bool B_MN, bool CF32>
+static int launch_gemm_2sm(const GemmParams& gp, int pairs, cudaStream_t stream) {
+    auto kern = gemm_tcgen05_2sm_kernel<A_MN, B_MN, CF32>;
+    static bool configured = false;
+    if (!configured) {
+        PK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Gemm2Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, gp));
+    count_launch();
+    return 0;
+}
+static int dispatch_2sm(const GemmParams& gp, int a_mn, int b_mn, int pairs, cudaStream_t stream) {
+#define PK_2SM(AM, BM_) (gp.c_is_f32 ? launch_gemm_2sm<AM, BM_, true>(gp, pairs, stream) : launch_gemm_2sm<AM, BM_, false>(gp, pairs, stream))
+    if (!a_mn && !b_mn) return PK_2SM(false, false);
+    if (!a_mn && b_mn) return PK_2SM(false, true);
+    if (a_mn && !b_mn) return PK_2SM(true, false);
+    return PK_2SM(true, true);
+#undef PK_2SM
+}
+
 template <int BN>
 static int dispatch_major(const GemmParams& gp, int a_mn, int b_mn, int grid, cudaStream_t stream) {
     if (gp.c_is_f32) {
@@ -409,6 +710,12 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
     if (bn == 0) bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     PK_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "block_n must be 64, 128 or 256");
 
+    // CTA-pair kernel for the large tiles: 256 x 256 per pair (needs M > 128 so that the second CTA has rows)
+    static int use_2sm = -1;
+    if (use_2sm < 0) { const char* e = getenv("PK_GEMM_2SM"); use_2sm = e ? atoi(e) : 1; }
+    const int want_2sm = d->two_sm < 0 ? 0 : (d->two_sm > 0 ? 1 : use_2sm);
+    const bool two_sm = want_2sm && bn == 256 && M > 128;
+
     static thread_local GemmParams gp;   // ~2.6 KB; filled per call, copied into the launch
     memset(&gp, 0, sizeof(gp));
     long long K = d->a_mn_major ? d->a[0].dim[1] : d->a[0].dim[0];
@@ -418,7 +725,7 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
         PK_CHECK_ARG(ka == K && kb == K, "all pairs must share the reduction extent K");
         int rc = make_map(&gp.a[i], d->a[i], 0, 64, d->a_mn_major ? 64 : BM, "A");
         if (rc) return rc;
-        rc = make_map(&gp.b[i], d->b[i], 0, 64, d->b_mn_major ? 64 : bn, "B");
+        rc = make_map(&gp.b[i], d->b[i], 0, 64, d->b_mn_major ? 64 : (two_sm ? bn / 2 : bn), "B");   // a CTA of a pair stages half of B
         if (rc) return rc;
         gp.a_off[i] = d->a_row_off[i];
         gp.b_off[i] = d->b_row_off[i];
@@ -493,6 +800,13 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
     }
     const long long num_tiles = out_tiles * gp.k_splits;
     PK_CHECK_ARG(num_tiles < (1ll << 31), "too many tiles");
+    if (two_sm) {
+        const long long tiles_m2 = (M + 255) / 256;
+        const long long units = tiles_m2 * gp.tiles_n * gp.zb0 * gp.zb1 * gp.k_splits;
+        int pairs = num_sms() / 2;
+        if (units < pairs) pairs = (int)units;
+        return dispatch_2sm(gp, d->a_mn_major, d->b_mn_major, pairs, stream);
+    }
     int grid = num_sms();
     if (num_tiles < grid) grid = (int)num_tiles;
     if (bn == 64) return dispatch_major<64>(gp, d->a_mn_major, d->b_mn_major, grid, stream);

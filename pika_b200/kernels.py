@@ -43,7 +43,7 @@ def _fill_view(v, t):
 
 def gemm(a, b, c, a_mn=False, b_mn=False, a_sel=(SEL_ZB0, SEL_ZB1), b_sel=(SEL_ZB0, SEL_ZB1), kz_count=1,
          a_row_off=None, b_row_off=None, alpha=1.0, bias=None, act=ACT_NONE, drop_p=0.0, drop_seed=0,
-         aux=None, aux_mode=AUX_NONE, aux_scale=1.0, accumulate=False, block_n=0, k_splits=0):
+         aux=None, aux_mode=AUX_NONE, aux_scale=1.0, accumulate=False, block_n=0, k_splits=0, two_sm=0):
     """C = epilogue(alpha * sum_p A_p @ B_p^T) on the tcgen05 tensor cores (include/pika_b200.h).
 
     a, b: a bf16 view or a list of views (pairs).  Views are torch tensors of <= 4 dims laid out
@@ -88,6 +88,7 @@ def gemm(a, b, c, a_mn=False, b_mn=False, a_sel=(SEL_ZB0, SEL_ZB1), b_sel=(SEL_Z
         d.aux_scale = aux_scale
     d.block_n = block_n
     d.k_splits = k_splits
+    d.two_sm = two_sm
     check(lib.pk_gemm_bf16(ctypes.byref(d), _stream()), "pk_gemm_bf16")
     return c
 
