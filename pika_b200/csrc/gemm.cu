@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_2sm_kernel(const
         }
         tma_prefetch_desc(&p.c);
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(&full_bar[s], 2);              // leader's expect_tx arrive + the peer producer's remote arrive
+            mbar_init(&full_bar[s], 1);              // leader's expect_tx arrive; the peer's loads are tracked by byte count only
             mbar_init(&empty_bar[s], 1);             // tcgen05.commit multicast
         }
         for (int a = 0; a < 2; ++a) {
@@ -417,7 +417,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_2sm_kernel(const
                     } else {
                         tma_load_4d_2sm(sb, &p.b[pr], &full_bar[stage], kb * BK, n0 + p.b_off[pr], b2, b3);
                     }
-                    if (rank != 0) mbar_arrive_remote(&full_bar[stage], 0);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
