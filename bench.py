@@ -104,6 +104,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+NCU_FC2_TRAFFIC_BYTES = 17.231e9   # dram__bytes_read.sum + dram__bytes_write.sum of one fc2 launch, ncu --set full capture
 CPU_THREADS_CAP = 32      # torch-CPU fp32 layers stop scaling (and oversubscribe) beyond a few dozen threads on the 128-core hosts
 
 
@@ -376,7 +377,10 @@ def run_ours(a):
                 "ms_per_step": ms_e2e / a.steps, "loss": last.get("loss")},
         "gpu_launches": launches,
         "roofline": {"kernel": "gemm_tcgen05_kernel (joint fc2 forward, M=%d N=%d K=%d)" % (R, a.V, H), "bound": "tensor",
-                     "achieved": g_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": g_tf / tf_burst, "traffic": None,
+                     "achieved": g_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": g_tf / tf_burst,
+                     "traffic": NCU_FC2_TRAFFIC_BYTES if (R, a.V, H) == (1159680, 6000, 1024) else None,
+                     "traffic_source": "profiles/r01_gemm_fc2.ncu.txt (dram read 3.36 GB + write 13.88 GB per launch; algorithmic: "
+                                       "A 2.38 GB + B 0.012 GB + C 13.92 GB)",
                      "launch_ms": g_ms},
         "roofline_loss": {"kernel": "rnnt_rowstats + rnnt_lattice + rnnt_grad (fused log-softmax + RNN-T loss + gradient)", "bound": "hbm",
                           "achieved": l_gbs, "peak": hbm, "unit": "GB/s", "frac": l_gbs / hbm, "traffic": None, "launch_ms": l_ms,
