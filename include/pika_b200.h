@@ -88,6 +88,10 @@ typedef struct {
     int block_n;                      /* 0 = auto; else 64 | 128 | 256 */
     int k_splits;                     /* 0 = auto; 1 = off; >1 = split the reduction (plain f32 2-D C only) */
     int two_sm;                       /* 0 = auto (CTA-pair kernel for 256-wide tiles when M > 128); 1 = force; -1 = never */
+    float* row_lse;                   /* optional out [ceil(N/block_n)][M][2] f32: per row and N-tile (max*log2(e), sum_j 2^(c_ij*log2(e) - max))
+                                         over the ROUNDED bf16 outputs -- the first pass of the fused log-softmax + RNN-T loss
+                                         (pk_rnnt_loss_fwd_bwd_lse) computed while the logits tile is still in TMEM.
+                                         Needs a 2-D bf16 C with N % 8 == 0; block_n is 256 unless forced. */
 } pk_gemm_desc;
 
 int pk_gemm_bf16(const pk_gemm_desc* desc, void* stream);
@@ -111,6 +115,12 @@ int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const
                          const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
                          const float* grad_scale, float* costs, void* dlogits, float* dlogits_colsum, void* workspace,
                          long long workspace_bytes, void* stream);
+/* Same, with the first pass (row log-sum-exp) already done by the GEMM that produced the logits:
+ * row_lse [n_parts][B*T*U1][2] as written through pk_gemm_desc.row_lse.  Saves one full read of the logits. */
+int pk_rnnt_loss_fwd_bwd_lse(const void* logits, int dtype, const int* labels, const int* frame_lens,
+                             const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
+                             const float* grad_scale, float* costs, void* dlogits, float* dlogits_colsum, void* workspace,
+                             long long workspace_bytes, const float* row_lse, int n_parts, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Memory-bound layers around the GEMMs (pika_b200/csrc/elementwise.cu).  `dtype` is the
@@ -120,6 +130,22 @@ int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const
  * weight/activation staging for pk_gemm_bf16 (replaces the implicit casts of torch autocast-free fp32). */
 int pk_cast_split(const void* src, int src_dtype, long long ld_src, void* hi, void* lo, long long ld_dst,
                   long long rows, int cols, int cols_pad, float scale, void* stream);
+/* dst[c, r] = src[r, c] for a bf16 matrix [rows, cols]: K-major copies of staged weights for the dgrad GEMMs
+ * (the reference relies on cuBLAS's transposed-operand modes, e.g. nn.Linear backward). */
+int pk_transpose_bf16(const void* src, long long ld_src, void* dst, long long ld_dst, int rows, int cols, void* stream);
+/* Fused unmasked multi-head self-attention, head dim 64, bf16 (pika_b200/csrc/attention.cu):
+ *   O = dropout(softmax(alpha * Q K^T)) V  per (batch, head)   -- MultiHeadedAttention.forward,
+ *   trainer/model/modules/multi_headed_attn.py:199-223 (scale, softmax, dropout, context) and its autograd backward,
+ * without materialising the [B, heads, T, T] score / probability tensors.
+ *   q, k, v: element (b, t, h, d) at ptr[(b*T + t)*ld_qkv + h*64 + d]  (three column blocks of a fused [B,T,3D] projection)
+ *   out / dout [B, T, heads*64] with row strides ld_out / ld_dout;  lse [B*heads*T] f32 saved for the backward
+ *   dq, dk, dv: same addressing with row stride ld_dqkv;  dsum_ws: B*heads*T floats of scratch
+ * Dropout masks are the same counter-based masks as pk_softmax_fwd/bwd for equal (drop_p, seed). */
+int pk_attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, float* lse,
+                     int B, int T, int heads, int dh, float alpha, float drop_p, uint32_t seed, void* stream);
+int pk_attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
+                     const void* dout, long long ld_dout, const float* lse, float* dsum_ws, void* dq, void* dk, void* dv,
+                     long long ld_dqkv, int B, int T, int heads, int dh, float alpha, float drop_p, uint32_t seed, void* stream);
 /* nn.BatchNorm1d over rows [rows, C] (trainer/model/rnnt_tdnn_transformer.py:41,58-59,69,76-82,85):
  * train: batch statistics incl. padded frames, running stats updated (momentum 0.1); eval: running stats.
  * stats_ws: pk_colstats_ws_floats(C) + 2*C floats scratch.  mean/rstd [C] are saved for the backward. */

@@ -50,6 +50,7 @@ class GemmDesc(ctypes.Structure):
         ("block_n", ctypes.c_int),
         ("k_splits", ctypes.c_int),
         ("two_sm", ctypes.c_int),
+        ("row_lse", ctypes.c_void_p),
     ]
 
 
@@ -76,6 +77,7 @@ def _sig(name, argtypes, restype=ctypes.c_int):
 _sig("pk_gemm_bf16", [ctypes.POINTER(GemmDesc), _vp])
 _sig("pk_rnnt_loss_workspace_bytes", [_i, _i, _i], ctypes.c_longlong)
 _sig("pk_rnnt_loss_fwd_bwd", [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _ll, _vp])
+_sig("pk_rnnt_loss_fwd_bwd_lse", [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _i, _vp])
 
 
 def check(rc, what=""):

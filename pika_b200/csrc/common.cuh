@@ -45,6 +45,11 @@ PK_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+PK_DEVICE float ex2_approx(float x) {            // 2^x on the MUFU, flush-to-zero, no range fix-up (2^-inf = 0)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 PK_DEVICE float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 PK_DEVICE float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 

@@ -48,6 +48,7 @@ struct GemmParams {
     const void* aux;
     long long aux_sm, aux_s0, aux_s1;
     float aux_scale;
+    float* row_lse;                     // optional [tiles_n][M][2] per-row (max*log2e, sum 2^(x*log2e-max)) partials of the bf16 output
 };
 
 template <int BN> struct GemmCfg {
@@ -65,7 +66,9 @@ PK_DEVICE int pick_sel(int sel, int zb0, int zb1, int kz) {
     return sel == PK_SEL_ZB0 ? zb0 : (sel == PK_SEL_ZB1 ? zb1 : (sel == PK_SEL_KZ ? kz : 0));
 }
 
-template <bool A_MN, bool B_MN, int BN, bool CF32>
+// WIDE: the epilogue pulls 32 accumulator columns per tcgen05.ld (one wait per 32 columns instead of one per 4/8);
+// the narrow variant is kept for A/B runs (PK_GEMM_EPI_WIDE=0).
+template <bool A_MN, bool B_MN, int BN, bool CF32, bool WIDE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 aux_row = reinterpret_cast<const unsigned char*>(p.aux) + off * (p.aux_is_f32 ? 4 : 2);
             }
             const uint64_t lin_row = ((uint64_t)(zb1 * p.zb0 + zb0) * (uint64_t)p.M + (uint64_t)m) * (uint64_t)p.N;
+            float lse_m = -INFINITY, lse_s = 0.f;   // running row max (log2 units) and sum over this tile's columns
             constexpr int n_chunks = BN / CH;
             for (int ch = 0; ch < n_chunks; ++ch) {
                 const int nc0 = n0 + ch * CH;
@@ -236,12 +240,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 if (store_thread) tma_store_wait_read<1>();     // the buffer used two chunks ago is free
                 named_bar_sync(1, 128);
                 uint8_t* srow = sbuf + row * 128;
-#pragma unroll 2
-                for (int gq = 0; gq < 8; ++gq) {
-                    uint32_t rr[GW];
-                    if (CF32) tmem_ld_32x4(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[4]>(&rr[0]));
-                    else tmem_ld_32x8(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[8]>(&rr[0]));
-                    tmem_ld_wait();
+                auto do_group = [&](const uint32_t (&rr)[GW], const int gq) {
                     const int ncol = nc0 + gq * GW;
                     float x[GW];
                     const float* bsm = bias_smem + ch * CH + gq * GW;
@@ -285,8 +284,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                     } else {
                         w.x = pack_bf16x2(x[0], x[1]); w.y = pack_bf16x2(x[2], x[3]);
                         w.z = pack_bf16x2(x[GW - 4], x[GW - 3]); w.w = pack_bf16x2(x[GW - 2], x[GW - 1]);
+                        if (p.row_lse != nullptr && ncol < p.N) {
+                            // online log-sum-exp over the ROUNDED values (what the consumer of C will read); N % 8 == 0
+                            float r[8];
+                            r[0] = bf16lo(w.x); r[1] = bf16hi(w.x); r[2] = bf16lo(w.y); r[3] = bf16hi(w.y);
+                            r[4] = bf16lo(w.z); r[5] = bf16hi(w.z); r[6] = bf16lo(w.w); r[7] = bf16hi(w.w);
+                            float gm = fmaxf(fmaxf(fmaxf(r[0], r[1]), fmaxf(r[2], r[3])), fmaxf(fmaxf(r[4], r[5]), fmaxf(r[6], r[7])));
+                            const float m_new = fmaxf(lse_m, gm * 1.4426950408889634f);
+                            // raw MUFU.EX2 (no denormal fix-up sequence): eight independent exponentials issue back to back
+                            float ex[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) ex[e] = ex2_approx(fmaf(r[e], 1.4426950408889634f, -m_new));
+                            const float acc = ((ex[0] + ex[1]) + (ex[2] + ex[3])) + ((ex[4] + ex[5]) + (ex[6] + ex[7]));
+                            lse_s = fmaf(lse_s, ex2_approx(lse_m - m_new), acc);
+                            lse_m = m_new;
+                        }
                     }
                     *reinterpret_cast<uint4*>(srow + ((gq ^ (row & 7)) << 4)) = w;
+                };
+                if (WIDE) {
+#pragma unroll 1
+                    for (int part = 0; part < CH / 32; ++part) {
+                        uint32_t r32[32];
+                        tmem_ld_32x32(t_addr + ch * CH + part * 32, r32);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g4 = 0; g4 < 32 / GW; ++g4) {
+                            uint32_t rr[GW];
+#pragma unroll
+                            for (int e = 0; e < GW; ++e) rr[e] = r32[g4 * GW + e];
+                            do_group(rr, part * (32 / GW) + g4);
+                        }
+                    }
+                } else {
+#pragma unroll 2
+                    for (int gq = 0; gq < 8; ++gq) {
+                        uint32_t rr[GW];
+                        if (CF32) tmem_ld_32x4(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[4]>(&rr[0]));
+                        else tmem_ld_32x8(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[8]>(&rr[0]));
+                        tmem_ld_wait();
+                        do_group(rr, gq);
+                    }
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, 128);
@@ -297,6 +335,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 }
                 ++chunk_ctr;
             }
+            if (!CF32 && p.row_lse != nullptr && row_ok)
+                *reinterpret_cast<float2*>(p.row_lse + ((size_t)nb * (size_t)p.M + (size_t)m) * 2) = make_float2(lse_m, lse_s);
             // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
             tc_fence_before();
             __syncwarp();
@@ -632,9 +672,9 @@ static int make_map(CUtensorMap* out, const pk_view4& v, int is_f32, int box0, i
 
 void count_launch();
 
-template <bool A_MN, bool B_MN, int BN, bool CF32>
-static int launch_gemm(const GemmParams& gp, int grid, cudaStream_t stream) {
-    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, CF32>;
+template <bool A_MN, bool B_MN, int BN, bool CF32, bool WIDE>
+static int launch_gemm_w(const GemmParams& gp, int grid, cudaStream_t stream) {
+    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, CF32, WIDE>;
     static bool configured = false;
     if (!configured) {
         PK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
@@ -644,6 +684,13 @@ static int launch_gemm(const GemmParams& gp, int grid, cudaStream_t stream) {
     PK_CHECK_LAUNCH();
     count_launch();
     return 0;
+}
+
+template <bool A_MN, bool B_MN, int BN, bool CF32>
+static int launch_gemm(const GemmParams& gp, int grid, cudaStream_t stream) {
+    static int wide = -1;                                   // tuning hook: PK_GEMM_EPI_WIDE=0 selects the narrow-load epilogue
+    if (wide < 0) { const char* e = getenv("PK_GEMM_EPI_WIDE"); wide = e ? atoi(e) : 1; }
+    return wide ? launch_gemm_w<A_MN, B_MN, BN, CF32, true>(gp, grid, stream) : launch_gemm_w<A_MN, B_MN, BN, CF32, false>(gp, grid, stream);
 }
 
 template <bool A_MN, bool B_MN, bool CF32>
@@ -715,6 +762,10 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
     const int want_2sm = d->two_sm < 0 ? 0 : (d->two_sm > 0 ? 1 : use_2sm);
     const bool two_sm = want_2sm && bn == 256 && M > 128;
 
+    {   // the tensor-map encoder is a driver-API call: make sure this host thread (e.g. an autograd worker) has the primary context bound
+        static thread_local bool ctx_ready = false;
+        if (!ctx_ready) { PK_CHECK_CUDA(cudaFree(nullptr)); ctx_ready = true; }
+    }
     static thread_local GemmParams gp;   // ~2.6 KB; filled per call, copied into the launch
     memset(&gp, 0, sizeof(gp));
     long long K = d->a_mn_major ? d->a[0].dim[1] : d->a[0].dim[0];
@@ -760,6 +811,9 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
     gp.aux = d->aux;
     gp.aux_sm = d->aux_stride[0]; gp.aux_s0 = d->aux_stride[1]; gp.aux_s1 = d->aux_stride[2];
     gp.aux_scale = d->aux_scale;
+    gp.row_lse = d->row_lse;
+    PK_CHECK_ARG(d->row_lse == nullptr || (d->c_dtype == PK_BF16 && N % 8 == 0 && gp.zb0 == 1 && gp.zb1 == 1 && !two_sm),
+                 "row_lse needs a 2-D bf16 C with N % 8 == 0 on the single-CTA kernel");
 
     const long long out_tiles = (long long)gp.tiles_m * gp.tiles_n * gp.zb0 * gp.zb1;
     // split-K: under-filled grids with a long reduction (wgrad, the LSTM's recurrent dgrad) are cut along the

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) rnnt_rowstats_kernel(const T* __restrict_
                     float f[VN];
                     Vec16<T>::unpack(q[k], f);
 #pragma unroll
-                    for (int e = 0; e < VN; ++e) s += exp2f(fmaf(f[e], kLog2e, -m));
+                    for (int e = 0; e < VN; ++e) s += ex2_approx(fmaf(f[e], kLog2e, -m));   // raw MUFU.EX2: no denormal fix-up sequence
                 }
             }
         }
@@ -139,6 +139,43 @@ __global__ void __launch_bounds__(256) rnnt_rowstats_kernel(const T* __restrict_
                 const int y = labels[(size_t)b * d.ld_labels + u];
                 lpl_skew[sk] = to_f32<T>(rp[y]) - lse;
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ pass 1, fused variant
+// The producing GEMM already reduced every logits row to per-N-tile (max, sum) pairs (pk_gemm_desc.row_lse);
+// this kernel only merges the n_parts pairs of a row and gathers the blank / label logits: ~100 bytes per row
+// instead of a full read of the row.
+template <typename T>
+__global__ void __launch_bounds__(256) rnnt_rowfinish_kernel(const T* __restrict__ logits, const int* __restrict__ labels,
+                                                             const int* __restrict__ frame_lens, const int* __restrict__ label_lens,
+                                                             RnntDims d, const float2* __restrict__ parts, int n_parts,
+                                                             float* __restrict__ lse_out, float* __restrict__ lpb_skew,
+                                                             float* __restrict__ lpl_skew) {
+    const long long rows = (long long)d.B * d.T * d.U1;
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (long long)gridDim.x * blockDim.x) {
+        const int u = (int)(row % d.U1);
+        const long long bt = row / d.U1;
+        const int t = (int)(bt % d.T);
+        const int b = (int)(bt / d.T);
+        const int Tn = frame_lens[b], Un = label_lens[b];
+        if (t >= Tn || u > Un) continue;
+        float m = -INFINITY;
+        for (int i = 0; i < n_parts; ++i) m = fmaxf(m, parts[(size_t)i * rows + row].x);
+        float sum = 0.f;
+        for (int i = 0; i < n_parts; ++i) {
+            const float2 ps = parts[(size_t)i * rows + row];
+            sum += ps.y * exp2f(ps.x - m);
+        }
+        const float lse = (m + log2f(sum)) * kLn2;
+        const T* rp = logits + row * (long long)d.ldv;
+        lse_out[row] = lse;
+        const size_t sk = skew_index(d, b, t, u);
+        lpb_skew[sk] = to_f32<T>(rp[0]) - lse;
+        if (u < Un) {
+            const int y = labels[(size_t)b * d.ld_labels + u];
+            lpl_skew[sk] = to_f32<T>(rp[y]) - lse;
         }
     }
 }
@@ -379,7 +416,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, MINB) rnnt_grad_kernel(const T* 
                     float f[VN];
                     Vec16<T>::unpack(q[k][gq], f);
 #pragma unroll
-                    for (int e = 0; e < VN; ++e) f[e] = exp2f(fmaf(f[e], kLog2e, -l2)) * gsum;
+                    for (int e = 0; e < VN; ++e) f[e] = ex2_approx(fmaf(f[e], kLog2e, -l2)) * gsum;
                     const int v0 = i * VN;
                     if (v0 == 0) f[0] += gb;                                   // blank column
                     if (y >= v0 && y < v0 + VN) {                              // label column (one thread per row)
@@ -423,10 +460,10 @@ extern "C" long long pk_rnnt_loss_workspace_bytes(int B, int T, int U1) {
     return (2 * skew + 3 * nodes) * 4 + 2 * skew * 8 + 256;
 }
 
-extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const int* frame_lens,
-                                    const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
-                                    const float* grad_scale, float* costs, void* dlogits, float* dlogits_colsum, void* workspace,
-                                    long long workspace_bytes, void* stream_v) {
+static int rnnt_loss_impl(const void* logits, int dtype, const int* labels, const int* frame_lens,
+                          const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
+                          const float* grad_scale, float* costs, void* dlogits, float* dlogits_colsum, void* workspace,
+                          long long workspace_bytes, const float* row_lse, int n_parts, void* stream_v) {
     using namespace pk;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     PK_CHECK_ARG(dtype == PK_F32 || dtype == PK_BF16, "bad dtype");
@@ -448,7 +485,17 @@ extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* la
     long long want = (rows + warps_per_cta - 1) / warps_per_cta;
     const long long cap = (long long)num_sms() * 8 * 4;      // persistent grid-stride: 8 CTAs/SM x 4 waves
     const int grid = (int)(want < cap ? want : cap);
-    if (dtype == PK_BF16)
+    if (row_lse != nullptr) {
+        PK_CHECK_ARG(n_parts >= 1, "n_parts must be >= 1");
+        const int fgrid = (int)((rows + 255) / 256 < (long long)num_sms() * 8 ? (rows + 255) / 256 : (long long)num_sms() * 8);
+        if (dtype == PK_BF16)
+            rnnt_rowfinish_kernel<__nv_bfloat16><<<fgrid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), labels, frame_lens,
+                                                                           label_lens, d, reinterpret_cast<const float2*>(row_lse), n_parts,
+                                                                           lse, lpb, lpl);
+        else
+            rnnt_rowfinish_kernel<float><<<fgrid, 256, 0, stream>>>(reinterpret_cast<const float*>(logits), labels, frame_lens, label_lens, d,
+                                                                   reinterpret_cast<const float2*>(row_lse), n_parts, lse, lpb, lpl);
+    } else if (dtype == PK_BF16)
         rnnt_rowstats_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), labels,
                                                                      frame_lens, label_lens, d, lse, lpb, lpl);
     else
@@ -491,4 +538,21 @@ extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* la
         PK_CHECK_LAUNCH(); count_launch();
     }
     return 0;
+}
+
+extern "C" int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const int* frame_lens,
+                                    const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
+                                    const float* grad_scale, float* costs, void* dlogits, float* dlogits_colsum, void* workspace,
+                                    long long workspace_bytes, void* stream) {
+    return rnnt_loss_impl(logits, dtype, labels, frame_lens, label_lens, B, T, U1, V, ldv, ld_labels, grad_scale, costs, dlogits,
+                          dlogits_colsum, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+extern "C" int pk_rnnt_loss_fwd_bwd_lse(const void* logits, int dtype, const int* labels, const int* frame_lens,
+                                        const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
+                                        const float* grad_scale, float* costs, void* dlogits, float* dlogits_colsum, void* workspace,
+                                        long long workspace_bytes, const float* row_lse, int n_parts, void* stream) {
+    PK_CHECK_ARG(row_lse != nullptr, "row_lse is null");
+    return rnnt_loss_impl(logits, dtype, labels, frame_lens, label_lens, B, T, U1, V, ldv, ld_labels, grad_scale, costs, dlogits,
+                          dlogits_colsum, workspace, workspace_bytes, row_lse, n_parts, stream);
 }

@@ -15,6 +15,7 @@ trainer/model/rnnt_tdnn_transformer.py:73-89, trainer/model/modules/{transformer
 multi_headed_attn.py:110-241, position_ffn.py:27-39}.
 """
 import math
+import os
 
 import torch
 
@@ -103,6 +104,44 @@ def stage_weight(params, cols_pad=None, scale=None):
     parts = [hi] if lo is None else [hi, lo]
     _wcache[key] = (stamp, parts)
     return parts
+
+
+# opt-in: same-box A/B of the full step showed no gain (88.2 vs 87.9 ms) although isolated dgrads are 5-18 % faster with a
+# K-major B on random data; the extra transposes cancel it (profiles/r01_notes.md)
+_DGRAD_KMAJOR = os.environ.get("PK_DGRAD_KMAJOR", "0") != "0"
+
+
+def transposed_parts(parts):
+    """Transposed bf16 copies [K, N] of staged weight parts [N, K] so a dgrad reads its B operand K-major
+    (measured 5-18 % faster than MN-major B, profiles/r01_notes.md).  The copy hangs off the staged tensor, so it
+    lives exactly as long as that staging does."""
+    out = []
+    for p in parts:
+        t = getattr(p, "_pk_transposed", None)
+        if t is None:
+            t = torch.empty(p.shape[1], p.shape[0], dtype=torch.bfloat16, device=p.device)
+            K.transpose_bf16(p, t)
+            p._pk_transposed = t
+        out.append(t)
+    return out
+
+
+def dgrad_b(parts, rows=None, cols=None):
+    """B operand of dx = dy @ W for staged W parts [N, K] (optionally the sub-block rows x cols):
+    returns (b_parts, b_mn)."""
+    if _DGRAD_KMAJOR and all(p.shape[0] % 8 == 0 for p in parts):
+        t = transposed_parts(parts)                      # [K, N]
+        if cols is not None:
+            t = [p[cols[0]:cols[1]] for p in t]
+        if rows is not None:
+            t = [p[:, rows[0]:rows[1]] for p in t]
+        return t, False
+    sub = parts
+    if rows is not None:
+        sub = [p[rows[0]:rows[1]] for p in sub]
+    if cols is not None:
+        sub = [p[:, cols[0]:cols[1]] for p in sub]
+    return sub, True
 
 
 def _cat_bias(params):
@@ -195,7 +234,8 @@ class LinearFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            gemm_parts([d_parts], [ctx.w_parts], dx, b_mn=True)
+            wb, wmn = dgrad_b(ctx.w_parts)
+            gemm_parts([d_parts], [wb], dx, b_mn=wmn)
             if dx.shape[1] != x.shape[1]:
                 dx = dx[:, :x.shape[1]]
         # dW_i = dpre[:, rows_i]^T x ; db_i = colsum(dpre)[rows_i]
@@ -254,12 +294,15 @@ class TdnnFn(torch.autograd.Function):
         dpre = torch.empty_like(y)
         K.mask_nz(dy.contiguous(), y, dpre, 1.0)
         d_parts = stage_act(dpre)
-        b_taps = [[p[:, k * C:(k + 1) * C] for p in ctx.w_parts] for k in range(3)]
+        b_taps, wmn = [], True
+        for k in range(3):
+            bt, wmn = dgrad_b(ctx.w_parts, cols=(k * C, (k + 1) * C))
+            b_taps.append(bt)
         dx = None
         if ctx.needs_input_grad[0]:
             if stride == 1:
                 dx = torch.empty_like(x)
-                gemm_parts([d_parts] * 3, b_taps, dx, b_mn=True, a_sel=(K.SEL_ZB0, K.SEL_ZERO),
+                gemm_parts([d_parts] * 3, b_taps, dx, b_mn=wmn, a_sel=(K.SEL_ZB0, K.SEL_ZERO),
                            b_sel=(K.SEL_ZERO, K.SEL_ZERO), a_row_off=[0, -dil, -2 * dil])
             else:
                 # rows tau = k*dil + t*stride of the three taps are disjoint when the residues differ
@@ -267,7 +310,7 @@ class TdnnFn(torch.autograd.Function):
                 dx = torch.zeros_like(x)
                 span = (t_out - 1) * stride + 1
                 for k in range(3):
-                    gemm_parts([d_parts], [b_taps[k]], dx[:, k * dil: k * dil + span: stride, :], b_mn=True,
+                    gemm_parts([d_parts], [b_taps[k]], dx[:, k * dil: k * dil + span: stride, :], b_mn=wmn,
                                a_sel=(K.SEL_ZB0, K.SEL_ZERO), b_sel=(K.SEL_ZERO, K.SEL_ZERO))
         gw = grad_of(ctx.weight).view(N, 3 * C)
         span = (t_out - 1) * stride + 1
@@ -324,6 +367,9 @@ class LayerNormFn(torch.autograd.Function):
         return dx, None, None, None
 
 
+_FUSED_ATTN = os.environ.get("PK_FUSED_ATTN", "1") != "0"
+
+
 class AttentionFn(torch.autograd.Function):
     """Unmasked multi-head self-attention on a fused QKV tensor [B,T,3D] (q | k | v blocks):
     softmax((Q/sqrt(d)) K^T) -> dropout -> V   (trainer/model/modules/multi_headed_attn.py:199-223)."""
@@ -333,6 +379,17 @@ class AttentionFn(torch.autograd.Function):
         B, T, D3 = qkv.shape
         D = D3 // 3
         dh = D // heads
+        ctx.fused = _FUSED_ATTN and qkv.dtype == torch.bfloat16 and dh == 64
+        if ctx.fused:
+            # scores / probabilities never leave the SM (pika_b200/csrc/attention.cu)
+            qkv = qkv.contiguous()
+            out = _new((B, T, D), like=qkv)
+            lse = torch.empty(B * heads * T, dtype=torch.float32, device=qkv.device)
+            alpha = 1.0 / math.sqrt(dh)
+            K.attention_fwd(qkv, out, lse, heads, alpha, drop_p, seed)
+            ctx.save_for_backward(qkv, out, lse)
+            ctx.meta = (B, T, D, heads, dh, 0, drop_p, seed, alpha)
+            return out
         Tp = (T + 7) // 8 * 8
         parts = stage_act(qkv)
 
@@ -357,6 +414,12 @@ class AttentionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.fused:
+            qkv, out, lse = ctx.saved_tensors
+            B, T, D, heads, dh, _, drop_p, seed, alpha = ctx.meta
+            dqkv = torch.empty_like(qkv)
+            K.attention_bwd(qkv, out, dout.contiguous(), lse, dqkv, heads, alpha, drop_p, seed)
+            return dqkv, None, None, None
         qkv, P = ctx.saved_tensors
         B, T, D, heads, dh, Tp, drop_p, seed, alpha = ctx.meta
         dout = dout.contiguous()
@@ -463,7 +526,8 @@ class LstmLayerFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            gemm_parts([dg_parts], [ctx.wih_parts], dx.permute(1, 0, 2), b_mn=True, a_sel=(K.SEL_ZB0, K.SEL_ZERO),
+            wb, wmn = dgrad_b(ctx.wih_parts)
+            gemm_parts([dg_parts], [wb], dx.permute(1, 0, 2), b_mn=wmn, a_sel=(K.SEL_ZB0, K.SEL_ZERO),
                        b_sel=(K.SEL_ZERO, K.SEL_ZERO))
         return dx, None, None, None, None, None, None
 
@@ -497,8 +561,14 @@ def _ldv(V):
     return (V + 7) // 8 * 8
 
 
-def _joint_forward(enc, pred, model):
-    """factored gated joint -> (logits [B,T,U1,ldv] act dtype, saved state)."""
+# opt-in: the extra exp2 work makes the fc2 epilogue longer than its 16-k-block main loop (+3.5 ms on the GEMM vs -2.4 ms
+# for the removed first pass of the loss, profiles/r01_notes.md); needs a cheaper epilogue before it pays
+_FUSED_LSE = os.environ.get("PK_FUSED_LSE", "0") != "0"
+
+
+def _joint_forward(enc, pred, model, want_lse=False):
+    """factored gated joint -> (logits [B,T,U1,ldv] act dtype, saved state).  ``want_lse``: the fc2 GEMM also
+    reduces every logits row to per-tile (max, sum-exp) pairs (state["row_lse"]) for the fused loss."""
     B, T, H = enc.shape
     U1 = pred.shape[1]
     V = model.fc2.weight.shape[0]
@@ -517,8 +587,12 @@ def _joint_forward(enc, pred, model):
     w2 = stage_weight(fc2.weight)
     logits = _new((B, T, U1, ldv), like=enc, zero=(ldv != V))
     h_parts = stage_act(h)
-    gemm_parts([h_parts], [w2], logits.view(R, ldv)[:, :V], bias=fc2.bias.detach())
-    state = dict(ex=ex, py=py, h_parts=h_parts, enc_parts=enc_parts, pred_parts=pred_parts, wx=wx, w2=w2, dims=(B, T, U1, H, V, ldv))
+    row_lse = None
+    if want_lse and _FUSED_LSE and logits.dtype == torch.bfloat16 and V % 8 == 0:
+        row_lse = torch.empty((V + 255) // 256, R, 2, dtype=torch.float32, device=enc.device)
+    gemm_parts([h_parts], [w2], logits.view(R, ldv)[:, :V], bias=fc2.bias.detach(), row_lse=row_lse,
+               **({"block_n": 256} if row_lse is not None else {}))
+    state = dict(row_lse=row_lse, ex=ex, py=py, h_parts=h_parts, enc_parts=enc_parts, pred_parts=pred_parts, wx=wx, w2=w2, dims=(B, T, U1, H, V, ldv))
     return logits, state
 
 
@@ -530,7 +604,8 @@ def _joint_backward(dlogits, st, model, need_enc=True, need_pred=True, db2=None)
     dl_parts = [p.view(R, ldv) for p in stage_act(dlogits)]
     dl_v = [p[:, :V] for p in dl_parts]
     dh = _new((R, H), like=dlogits)
-    gemm_parts([dl_v], [st["w2"]], dh, b_mn=True)
+    w2b, w2mn = dgrad_b(st["w2"])
+    gemm_parts([dl_v], [w2b], dh, b_mn=w2mn)
     gemm_parts([dl_v], [st["h_parts"]], grad_of(fc2.weight), a_mn=True, b_mn=True)
     if db2 is None:
         db2 = torch.empty(ldv, dtype=torch.float32, device=dlogits.device)
@@ -552,11 +627,13 @@ def _joint_backward(dlogits, st, model, need_enc=True, need_pred=True, db2=None)
     d_enc = d_pred = None
     if need_enc:
         d_enc = _new((B * T, H), like=dlogits)
-        gemm_parts([dex_parts], [[p[:, :H] for p in st["wx"]]], d_enc, b_mn=True)
+        wb, wmn = dgrad_b(st["wx"], cols=(0, H))
+        gemm_parts([dex_parts], [wb], d_enc, b_mn=wmn)
         d_enc = d_enc.view(B, T, H)
     if need_pred:
         d_pred = _new((B * U1, H), like=dlogits)
-        gemm_parts([dpy_parts], [[p[:, H:] for p in st["wx"]]], d_pred, b_mn=True)
+        wb, wmn = dgrad_b(st["wx"], cols=(H, 2 * H))
+        gemm_parts([dpy_parts], [wb], d_pred, b_mn=wmn)
         d_pred = d_pred.view(B, U1, H)
     return d_enc, d_pred
 
@@ -584,10 +661,11 @@ class JointLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, pred, model, labels, frame_lens, label_lens):
-        logits, st = _joint_forward(enc, pred, model)
+        logits, st = _joint_forward(enc, pred, model, want_lse=True)
         V = st["dims"][4]
         db2 = torch.empty(logits.shape[-1], dtype=torch.float32, device=logits.device)
-        costs, _ = K.rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=V, dlogits=logits, colsum=db2)
+        costs, _ = K.rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=V, dlogits=logits, colsum=db2,
+                                       row_lse=st.pop("row_lse"))
         d_enc, d_pred = _joint_backward(logits, st, model, db2=db2)
         del logits, st
         ctx.save_for_backward(d_enc, d_pred)

@@ -43,7 +43,7 @@ def _fill_view(v, t):
 
 def gemm(a, b, c, a_mn=False, b_mn=False, a_sel=(SEL_ZB0, SEL_ZB1), b_sel=(SEL_ZB0, SEL_ZB1), kz_count=1,
          a_row_off=None, b_row_off=None, alpha=1.0, bias=None, act=ACT_NONE, drop_p=0.0, drop_seed=0,
-         aux=None, aux_mode=AUX_NONE, aux_scale=1.0, accumulate=False, block_n=0, k_splits=0, two_sm=0):
+         aux=None, aux_mode=AUX_NONE, aux_scale=1.0, accumulate=False, block_n=0, k_splits=0, two_sm=0, row_lse=None):
     """C = epilogue(alpha * sum_p A_p @ B_p^T) on the tcgen05 tensor cores (include/pika_b200.h).
 
     a, b: a bf16 view or a list of views (pairs).  Views are torch tensors of <= 4 dims laid out
@@ -89,12 +89,20 @@ def gemm(a, b, c, a_mn=False, b_mn=False, a_sel=(SEL_ZB0, SEL_ZB1), b_sel=(SEL_Z
     d.block_n = block_n
     d.k_splits = k_splits
     d.two_sm = two_sm
+    if row_lse is not None:
+        bn = block_n or (64 if c.shape[-1] <= 64 else (128 if c.shape[-1] <= 128 else 256))
+        assert row_lse.dtype == torch.float32 and row_lse.is_contiguous()
+        assert tuple(row_lse.shape) == ((c.shape[-1] + bn - 1) // bn, c.shape[-2], 2) and c.dim() == 2
+        d.row_lse = row_lse.data_ptr()
+        d.two_sm = -1
     check(lib.pk_gemm_bf16(ctypes.byref(d), _stream()), "pk_gemm_bf16")
     return c
 
 
-def rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=None, grad_scale=None, dlogits=None, want_grad=True, colsum=None):
-    """logits [B,T,U1,ldv] (bf16|f32) -> (costs [B] f32, dlogits).  dlogits may alias logits."""
+def rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=None, grad_scale=None, dlogits=None, want_grad=True, colsum=None,
+                      row_lse=None):
+    """logits [B,T,U1,ldv] (bf16|f32) -> (costs [B] f32, dlogits).  dlogits may alias logits.
+    row_lse [n_parts, B*T*U1, 2]: per-row log-sum-exp partials written by the producing GEMM (skips the first pass)."""
     B, T, U1, ldv = logits.shape
     V = ldv if V is None else V
     assert logits.is_contiguous() and labels.dtype == torch.int32 and labels.dim() == 2
@@ -104,6 +112,13 @@ def rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=None, grad_scale
     costs = torch.empty(B, dtype=torch.float32, device=logits.device)
     if want_grad and dlogits is None:
         dlogits = torch.empty_like(logits)
+    if row_lse is not None:
+        assert row_lse.dtype == torch.float32 and row_lse.is_contiguous() and tuple(row_lse.shape[1:]) == (B * T * U1, 2)
+        check(lib.pk_rnnt_loss_fwd_bwd_lse(_ptr(logits), _dt(logits), _ptr(labels), _ptr(frame_lens), _ptr(label_lens),
+                                           B, T, U1, V, ldv, max(labels.stride(0), 1), _ptr(grad_scale), _ptr(costs),
+                                           _ptr(dlogits if want_grad else None), _ptr(colsum), _ptr(ws), ws_bytes,
+                                           _ptr(row_lse), int(row_lse.shape[0]), _stream()), "pk_rnnt_loss_fwd_bwd_lse")
+        return costs, dlogits
     check(lib.pk_rnnt_loss_fwd_bwd(_ptr(logits), _dt(logits), _ptr(labels), _ptr(frame_lens), _ptr(label_lens),
                                    B, T, U1, V, ldv, max(labels.stride(0), 1), _ptr(grad_scale), _ptr(costs),
                                    _ptr(dlogits if want_grad else None), _ptr(colsum), _ptr(ws), ws_bytes, _stream()),
@@ -127,6 +142,39 @@ def cast_split(src, hi, lo=None, cols_pad=None, scale=1.0):
     assert hi.shape[-1] == cols_pad and hi.stride(-1) == 1 and src.stride(-1) == 1
     check(lib.pk_cast_split(_P(src), _I(_dt(src)), _L(src.stride(0)), _P(hi), _P(lo), _L(hi.stride(0)), _L(rows),
                             _I(cols), _I(cols_pad), _F(scale), _stream()), "pk_cast_split")
+
+
+def transpose_bf16(src, dst):
+    """dst [cols, rows] = src [rows, cols]^T (bf16, row strides free)"""
+    rows, cols = src.shape
+    assert src.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and dst.shape == (cols, rows)
+    assert src.stride(1) == 1 and dst.stride(1) == 1
+    check(lib.pk_transpose_bf16(_P(src), _L(src.stride(0)), _P(dst), _L(dst.stride(0)), _I(rows), _I(cols), _stream()),
+          "pk_transpose_bf16")
+
+
+def attention_fwd(qkv, out, lse, heads, alpha, drop_p=0.0, seed=0):
+    """qkv [B,T,3D] bf16 (q | k | v column blocks) -> out [B,T,D], lse [B*heads*T] f32 (fused attention, head dim 64)"""
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and out.is_contiguous() and out.shape == (B, T, D)
+    assert lse.dtype == torch.float32 and lse.numel() == B * heads * T
+    base, es = qkv.data_ptr(), 2
+    vp = ctypes.c_void_p
+    check(lib.pk_attention_fwd(vp(base), vp(base + D * es), vp(base + 2 * D * es), _L(D3), _P(out), _L(D), _P(lse), _I(B), _I(T),
+                               _I(heads), _I(D // heads), _F(alpha), _F(drop_p), _U(seed & 0xFFFFFFFF), _stream()), "pk_attention_fwd")
+
+
+def attention_bwd(qkv, out, dout, lse, dqkv, heads, alpha, drop_p=0.0, seed=0):
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    assert dout.is_contiguous() and dqkv.is_contiguous() and dqkv.shape == qkv.shape and dout.dtype == torch.bfloat16
+    ws = torch.empty(B * heads * T, dtype=torch.float32, device=qkv.device)
+    base, gb, es = qkv.data_ptr(), dqkv.data_ptr(), 2
+    vp = ctypes.c_void_p
+    check(lib.pk_attention_bwd(vp(base), vp(base + D * es), vp(base + 2 * D * es), _L(D3), _P(out), _L(D), _P(dout), _L(D), _P(lse), _P(ws),
+                               vp(gb), vp(gb + D * es), vp(gb + 2 * D * es), _L(D3), _I(B), _I(T), _I(heads), _I(D // heads), _F(alpha),
+                               _F(drop_p), _U(seed & 0xFFFFFFFF), _stream()), "pk_attention_bwd")
 
 
 _col_ws = {}

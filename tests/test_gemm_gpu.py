@@ -180,3 +180,50 @@ def test_gemm_split_bf16_fp32_class():
     K().gemm([ah, ah, al], [bh, bl, bh], c)
     ref = (af.double() @ bf.double().t()).float()
     assert rel(c, ref) < 3e-5
+
+
+@pytest.mark.parametrize("mnk", [(300, 6000, 256), (128, 256, 64), (1000, 520, 192)])
+def test_gemm_row_lse_partials(mnk):
+    """pk_gemm_desc.row_lse: per-row, per-N-tile (max*log2e, sum 2^(x*log2e-max)) of the ROUNDED bf16 outputs."""
+    import math
+    M, N, Kd = mnk
+    a, b = rnd(M, Kd, seed=11, scale=0.5), rnd(N, Kd, seed=12, scale=0.5)
+    bias = torch.randn(N, device="cuda")
+    c = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    nt = (N + 255) // 256
+    parts = torch.full((nt, M, 2), float("nan"), device="cuda")
+    K().gemm(a, b, c, bias=bias, block_n=256, row_lse=parts)
+    ref = a.float() @ b.float().t() + bias
+    assert rel(c, ref) < 4e-3
+    m = parts[:, :, 0].max(0).values
+    s = (parts[:, :, 1] * torch.exp2(parts[:, :, 0] - m)).sum(0)
+    lse = (m + torch.log2(s)) * math.log(2.0)
+    want = torch.logsumexp(c.float(), -1)               # of the rounded outputs, as the loss kernels read them
+    assert (lse - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
+    # every tile's partial alone equals the log-sum-exp of its own column block
+    for i in range(nt):
+        blk = c[:, i * 256:(i + 1) * 256].float()
+        got = (parts[i, :, 0] + torch.log2(parts[i, :, 1])) * math.log(2.0)
+        assert (got - torch.logsumexp(blk, -1)).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("mnk,a_mn,b_mn,ks", [((300, 520, 4096), 0, 0, 0), ((304, 520, 4096), 1, 1, 0), ((1664, 3072, 1024), 0, 0, 0),
+                                               ((1664, 3072, 1024), 1, 1, 0), ((128 * 37, 1024, 2048), 0, 1, 2), ((6000, 1024, 9000), 1, 1, 0),
+                                               ((4096, 1024, 4832), 1, 1, 0), ((200, 136, 1000), 0, 0, 7)])
+def test_gemm_split_k(mnk, a_mn, b_mn, ks):
+    """split-K over the flattened reduction (auto heuristic or forced): partial tiles meet in C via TMA reduce-add;
+    the result must equal the plain product, also when accumulating into a pre-filled C."""
+    M, N, Kd = mnk
+    a = rnd(Kd, M, seed=31) if a_mn else rnd(M, Kd, seed=31)
+    b = rnd(Kd, N, seed=32) if b_mn else rnd(N, Kd, seed=32)
+    ref = (a.float().t() if a_mn else a.float()) @ (b.float() if b_mn else b.float().t())
+    c = torch.full((M, N), float("nan"), device="cuda")
+    K().gemm(a, b, c, a_mn=bool(a_mn), b_mn=bool(b_mn), k_splits=ks)
+    assert rel(c, ref) < 2e-5
+    c0 = torch.randn(M, N, device="cuda")
+    c = c0.clone()
+    K().gemm(a, b, c, a_mn=bool(a_mn), b_mn=bool(b_mn), k_splits=ks, accumulate=True)
+    assert rel(c, ref + c0) < 2e-5
+    c = torch.full((M, N), float("nan"), device="cuda")
+    K().gemm(a, b, c, a_mn=bool(a_mn), b_mn=bool(b_mn), k_splits=1)          # forced off: same answer
+    assert rel(c, ref) < 2e-5

@@ -310,3 +310,86 @@ def test_lstm_persistent_kernel_bf16(B, U, H):
     out.backward(dy.to(torch.bfloat16))
     for p, gr, name in zip(params, gs, ["emb"] + [n for n, _ in lstm.named_parameters()]):
         assert rel(p.grad, gr) < 6e-2, (name, rel(p.grad, gr))
+
+
+def test_fused_lse_joint_loss_matches_separate_first_pass():
+    """bf16 production path: the fc2 GEMM's row-LSE partials + rnnt_rowfinish must reproduce the stand-alone first pass
+    (same rounded logits, only the fp32 summation order differs)."""
+    from pika_b200 import engine as E
+    H, V, B, T, U = 128, 520, 3, 13, 5
+    prev, was = E.get_precision(), E._FUSED_LSE
+    E.set_precision("bf16")
+    try:
+        class M(nn.Module):
+            pass
+        m = M()
+        m.fc1, m.fc_gate, m.fc2 = nn.Linear(2 * H, H).cuda(), nn.Linear(2 * H, H).cuda(), nn.Linear(H, V).cuda()
+        labels = torch.randint(1, V, (B, U), device="cuda").int()
+        fl = torch.tensor([T, T - 2, T - 5], dtype=torch.int32, device="cuda")
+        ll = torch.tensor([U, U - 1, 0], dtype=torch.int32, device="cuda")
+        res = []
+        for fused in (True, False):
+            E._FUSED_LSE = fused
+            enc = g(B, T, H, seed=26).bfloat16().requires_grad_(True)
+            pred = g(B, U + 1, H, seed=27).bfloat16().requires_grad_(True)
+            params = [enc, pred] + [p for l in (m.fc1, m.fc_gate, m.fc2) for p in l.parameters()]
+            for p in params:
+                p.grad = None
+            costs = E.JointLossFn.apply(enc, pred, m, labels, fl, ll)
+            costs.sum().backward()
+            res.append((costs.detach().clone(), [p.grad.detach().float().clone() for p in params]))
+        assert torch.allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-4)
+        for a, b in zip(res[0][1], res[1][1]):
+            assert rel(a, b) < 5e-3          # bf16 activation grads re-round; parameter grads agree far tighter
+        for a, b in zip(res[0][1][2:], res[1][1][2:]):
+            assert rel(a, b) < 2e-4
+    finally:
+        E._FUSED_LSE = was
+        E.set_precision(prev)
+
+
+@pytest.mark.parametrize("heads,T,B", [(4, 50, 2), (2, 200, 2), (16, 333, 1), (1, 64, 1), (3, 129, 2)])
+def test_fused_attention_bf16_matches_torch(heads, T, B):
+    """bf16 production path, head dim 64: attention.cu (scores stay on chip) vs fp32 torch on the same bf16 inputs."""
+    from pika_b200 import engine as E
+    D = heads * 64
+    prev = E.get_precision()
+    E.set_precision("bf16")
+    try:
+        assert E._FUSED_ATTN
+        qkv = g(B, T, 3 * D, seed=40).bfloat16().requires_grad_(True)
+        out = E.AttentionFn.apply(qkv, heads, 0.0, 0)
+        x = qkv.detach().float().requires_grad_(True)
+        q, k, v = (x[:, :, i * D:(i + 1) * D].view(B, T, heads, 64).transpose(1, 2) for i in range(3))
+        ref = torch.matmul(torch.softmax(torch.matmul(q / 8.0, k.transpose(2, 3)), -1), v).transpose(1, 2).reshape(B, T, D)
+        assert rel(out, ref) < 1e-2
+        dy = g(B, T, D, seed=41).bfloat16()
+        (gx,) = torch.autograd.grad(ref, [x], dy.float())
+        out.backward(dy)
+        for i, name in enumerate("qkv"):
+            assert rel(qkv.grad[:, :, i * D:(i + 1) * D], gx[:, :, i * D:(i + 1) * D]) < 2e-2, name
+    finally:
+        E.set_precision(prev)
+
+
+@pytest.mark.parametrize("drop_p", [0.0, 0.25])
+def test_fused_attention_matches_materialised_path(drop_p):
+    """same dropout masks (counter-based, indexed over the [B*heads*T, T] probability matrix) in both implementations"""
+    from pika_b200 import engine as E
+    B, T, heads = 2, 150, 4
+    D = heads * 64
+    prev = E.get_precision()
+    E.set_precision("bf16")
+    try:
+        res = []
+        for fused in (True, False):
+            E._FUSED_ATTN = fused
+            qkv = g(B, T, 3 * D, seed=42).bfloat16().requires_grad_(True)
+            out = E.AttentionFn.apply(qkv, heads, drop_p, 4242)
+            out.backward(g(B, T, D, seed=43).bfloat16())
+            res.append((out.detach().float(), qkv.grad.float()))
+        assert rel(res[0][0], res[1][0]) < 1e-2
+        assert rel(res[0][1], res[1][1]) < 2e-2
+    finally:
+        E._FUSED_ATTN = True
+        E.set_precision(prev)
