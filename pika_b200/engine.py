@@ -16,6 +16,7 @@ multi_headed_attn.py:110-241, position_ffn.py:27-39}.
 """
 import math
 import os
+import weakref
 
 import torch
 
@@ -81,6 +82,18 @@ def stage_act(x):
 _wcache = {}
 
 
+def _prune_wcache():
+    if len(_wcache) > 512:
+        for k in [k for k, v in _wcache.items() if any(r() is None for r in v[2])]:
+            del _wcache[k]
+
+
+def _same_objects(refs, params):
+    """id() values are recycled: a cache entry only counts if its weak references still point at these very tensors
+    (a freed parameter whose id, version and storage address all reappear would otherwise alias a stale staging)."""
+    return len(refs) == len(params) and all(r() is p for r, p in zip(refs, params))
+
+
 def stage_weight(params, cols_pad=None, scale=None):
     """Parameter(s) -> staged bf16 operand parts of the row-concatenated matrix [sum N_i, K(_pad)].
     Cached until the parameters change (torch version counter or ``invalidate_weights``)."""
@@ -88,7 +101,7 @@ def stage_weight(params, cols_pad=None, scale=None):
     key = (tuple(id(p) for p in params), _PRECISION, cols_pad)
     stamp = (tuple(p._version for p in params), _WEIGHT_EPOCH, tuple(p.data_ptr() for p in params))
     hit = _wcache.get(key)
-    if hit is not None and hit[0] == stamp:
+    if hit is not None and hit[0] == stamp and _same_objects(hit[2], params):
         return hit[1]
     mats = [p.detach().reshape(p.shape[0], -1) for p in params]
     Kdim = mats[0].shape[1]
@@ -102,7 +115,8 @@ def stage_weight(params, cols_pad=None, scale=None):
                      scale=1.0 if scale is None else scale[i])
         r += m.shape[0]
     parts = [hi] if lo is None else [hi, lo]
-    _wcache[key] = (stamp, parts)
+    _prune_wcache()
+    _wcache[key] = (stamp, parts, tuple(weakref.ref(p) for p in params))
     return parts
 
 
@@ -151,14 +165,14 @@ def _cat_bias(params):
     key = (tuple(id(p) for p in params), "bias")
     stamp = (tuple(p._version for p in params), _WEIGHT_EPOCH, tuple(p.data_ptr() for p in params))
     hit = _wcache.get(key)
-    if hit is not None and hit[0] == stamp:
+    if hit is not None and hit[0] == stamp and _same_objects(hit[2], params):
         return hit[1]
     out = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
     r = 0
     for p in params:
         out[r:r + p.numel()].copy_(p.detach())
         r += p.numel()
-    _wcache[key] = (stamp, out)
+    _wcache[key] = (stamp, out, tuple(weakref.ref(p) for p in params))
     return out
 
 
