@@ -66,9 +66,12 @@ PK_DEVICE int pick_sel(int sel, int zb0, int zb1, int kz) {
     return sel == PK_SEL_ZB0 ? zb0 : (sel == PK_SEL_ZB1 ? zb1 : (sel == PK_SEL_KZ ? kz : 0));
 }
 
-// WIDE: the epilogue pulls 32 accumulator columns per tcgen05.ld (one wait per 32 columns instead of one per 4/8);
-// the narrow variant is kept for A/B runs (PK_GEMM_EPI_WIDE=0).
-template <bool A_MN, bool B_MN, int BN, bool CF32, bool WIDE>
+// EPI selects what the epilogue compiles in, so that the common case is straight-line code (the run-time-uniform
+// branches of the full epilogue cost an instruction-fetch bubble per 16-byte group, profiles/r01_notes.md):
+//   EPI_PLAIN  alpha, bias, ReLU only      EPI_LSE  + per-row log-sum-exp partials (bf16 C)      EPI_FULL  + dropout / aux add / aux mask
+// The epilogue pulls 32 accumulator columns per tcgen05.ld (one wait per 32 columns).
+enum { EPI_PLAIN = 0, EPI_LSE = 1, EPI_FULL = 2 };
+template <bool A_MN, bool B_MN, int BN, bool CF32, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -246,12 +249,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                     const float* bsm = bias_smem + ch * CH + gq * GW;
 #pragma unroll
                     for (int e = 0; e < GW; ++e) x[e] = fmaxf(fmaf(__uint_as_float(rr[e]), p.alpha, bsm[e]), relu_floor);
-                    if (p.drop_thresh != 0u) {
+                    if (EPI == EPI_FULL && p.drop_thresh != 0u) {
 #pragma unroll
                         for (int e = 0; e < GW; ++e)
                             x[e] = drop_keep(lin_row + (uint64_t)(ncol + e), p.drop_seed, p.drop_thresh) ? x[e] * p.drop_scale : 0.f;
                     }
-                    if (aux_row != nullptr && ncol < p.N) {       // N % GW == 0 is enforced on the host when aux is used
+                    if (EPI == EPI_FULL && aux_row != nullptr && ncol < p.N) {       // N % GW == 0 is enforced on the host when aux is used
                         float a[GW];
                         if (p.aux_is_f32) {
                             const float4* ap = reinterpret_cast<const float4*>(aux_row + (size_t)ncol * 4);
@@ -284,13 +287,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                     } else {
                         w.x = pack_bf16x2(x[0], x[1]); w.y = pack_bf16x2(x[2], x[3]);
                         w.z = pack_bf16x2(x[GW - 4], x[GW - 3]); w.w = pack_bf16x2(x[GW - 2], x[GW - 1]);
-                        if (p.row_lse != nullptr && ncol < p.N) {
-                            // online log-sum-exp over the ROUNDED values (what the consumer of C will read); N % 8 == 0
+                        if (EPI == EPI_LSE) {
+                            // online log-sum-exp over the ROUNDED values (what the consumer of C will read); N % 8 == 0, so a
+                            // group is valid or invalid as a whole: invalid groups are pushed to -inf instead of branching
+                            const float kill = (ncol < p.N) ? 0.f : -INFINITY;
                             float r[8];
-                            r[0] = bf16lo(w.x); r[1] = bf16hi(w.x); r[2] = bf16lo(w.y); r[3] = bf16hi(w.y);
-                            r[4] = bf16lo(w.z); r[5] = bf16hi(w.z); r[6] = bf16lo(w.w); r[7] = bf16hi(w.w);
-                            float gm = fmaxf(fmaxf(fmaxf(r[0], r[1]), fmaxf(r[2], r[3])), fmaxf(fmaxf(r[4], r[5]), fmaxf(r[6], r[7])));
-                            const float m_new = fmaxf(lse_m, gm * 1.4426950408889634f);
+                            r[0] = bf16lo(w.x) + kill; r[1] = bf16hi(w.x) + kill; r[2] = bf16lo(w.y) + kill; r[3] = bf16hi(w.y) + kill;
+                            r[4] = bf16lo(w.z) + kill; r[5] = bf16hi(w.z) + kill; r[6] = bf16lo(w.w) + kill; r[7] = bf16hi(w.w) + kill;
+                            const float gm = fmaxf(fmaxf(fmaxf(r[0], r[1]), fmaxf(r[2], r[3])), fmaxf(fmaxf(r[4], r[5]), fmaxf(r[6], r[7])));
+                            const float m_new = fmaxf(lse_m, gm * 1.4426950408889634f);   // finite: the first group of a tile is valid
                             // raw MUFU.EX2 (no denormal fix-up sequence): eight independent exponentials issue back to back
                             float ex[8];
 #pragma unroll
@@ -302,28 +307,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                     }
                     *reinterpret_cast<uint4*>(srow + ((gq ^ (row & 7)) << 4)) = w;
                 };
-                if (WIDE) {
 #pragma unroll 1
-                    for (int part = 0; part < CH / 32; ++part) {
-                        uint32_t r32[32];
-                        tmem_ld_32x32(t_addr + ch * CH + part * 32, r32);
-                        tmem_ld_wait();
+                for (int part = 0; part < CH / 32; ++part) {
+                    uint32_t r32[32];
+                    tmem_ld_32x32(t_addr + ch * CH + part * 32, r32);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int g4 = 0; g4 < 32 / GW; ++g4) {
-                            uint32_t rr[GW];
-#pragma unroll
-                            for (int e = 0; e < GW; ++e) rr[e] = r32[g4 * GW + e];
-                            do_group(rr, part * (32 / GW) + g4);
-                        }
-                    }
-                } else {
-#pragma unroll 2
-                    for (int gq = 0; gq < 8; ++gq) {
+                    for (int g4 = 0; g4 < 32 / GW; ++g4) {
                         uint32_t rr[GW];
-                        if (CF32) tmem_ld_32x4(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[4]>(&rr[0]));
-                        else tmem_ld_32x8(t_addr + ch * CH + gq * GW, *reinterpret_cast<uint32_t (*)[8]>(&rr[0]));
-                        tmem_ld_wait();
-                        do_group(rr, gq);
+#pragma unroll
+                        for (int e = 0; e < GW; ++e) rr[e] = r32[g4 * GW + e];
+                        do_group(rr, part * (32 / GW) + g4);
                     }
                 }
                 fence_proxy_async_smem();
@@ -335,7 +329,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 }
                 ++chunk_ctr;
             }
-            if (!CF32 && p.row_lse != nullptr && row_ok)
+            if (!CF32 && EPI == EPI_LSE && row_ok)
                 *reinterpret_cast<float2*>(p.row_lse + ((size_t)nb * (size_t)p.M + (size_t)m) * 2) = make_float2(lse_m, lse_s);
             // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
             tc_fence_before();
@@ -672,9 +666,9 @@ static int make_map(CUtensorMap* out, const pk_view4& v, int is_f32, int box0, i
 
 void count_launch();
 
-template <bool A_MN, bool B_MN, int BN, bool CF32, bool WIDE>
-static int launch_gemm_w(const GemmParams& gp, int grid, cudaStream_t stream) {
-    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, CF32, WIDE>;
+template <bool A_MN, bool B_MN, int BN, bool CF32, int EPI>
+static int launch_gemm_e(const GemmParams& gp, int grid, cudaStream_t stream) {
+    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, CF32, EPI>;
     static bool configured = false;
     if (!configured) {
         PK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
@@ -688,9 +682,12 @@ static int launch_gemm_w(const GemmParams& gp, int grid, cudaStream_t stream) {
 
 template <bool A_MN, bool B_MN, int BN, bool CF32>
 static int launch_gemm(const GemmParams& gp, int grid, cudaStream_t stream) {
-    static int wide = -1;                                   // tuning hook: PK_GEMM_EPI_WIDE=0 selects the narrow-load epilogue
-    if (wide < 0) { const char* e = getenv("PK_GEMM_EPI_WIDE"); wide = e ? atoi(e) : 1; }
-    return wide ? launch_gemm_w<A_MN, B_MN, BN, CF32, true>(gp, grid, stream) : launch_gemm_w<A_MN, B_MN, BN, CF32, false>(gp, grid, stream);
+    if (gp.row_lse != nullptr) {
+        if (CF32) { set_last_error("gemm: row_lse needs a bf16 C"); return -1; }
+        return launch_gemm_e<A_MN, B_MN, BN, false, EPI_LSE>(gp, grid, stream);
+    }
+    if (gp.drop_thresh != 0u || gp.aux_mode != PK_AUX_NONE) return launch_gemm_e<A_MN, B_MN, BN, CF32, EPI_FULL>(gp, grid, stream);
+    return launch_gemm_e<A_MN, B_MN, BN, CF32, EPI_PLAIN>(gp, grid, stream);
 }
 
 template <bool A_MN, bool B_MN, bool CF32>
@@ -812,8 +809,9 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
     gp.aux_sm = d->aux_stride[0]; gp.aux_s0 = d->aux_stride[1]; gp.aux_s1 = d->aux_stride[2];
     gp.aux_scale = d->aux_scale;
     gp.row_lse = d->row_lse;
-    PK_CHECK_ARG(d->row_lse == nullptr || (d->c_dtype == PK_BF16 && N % 8 == 0 && gp.zb0 == 1 && gp.zb1 == 1 && !two_sm),
-                 "row_lse needs a 2-D bf16 C with N % 8 == 0 on the single-CTA kernel");
+    PK_CHECK_ARG(d->row_lse == nullptr || (d->c_dtype == PK_BF16 && N % 8 == 0 && gp.zb0 == 1 && gp.zb1 == 1 && !two_sm &&
+                                           gp.drop_thresh == 0u && gp.aux_mode == PK_AUX_NONE),
+                 "row_lse needs a 2-D bf16 C with N % 8 == 0, no dropout / aux, on the single-CTA kernel");
 
     const long long out_tiles = (long long)gp.tiles_m * gp.tiles_n * gp.zb0 * gp.zb1;
     // split-K: under-filled grids with a long reduction (wgrad, the LSTM's recurrent dgrad) are cut along the
