@@ -824,13 +824,18 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
         static int mode = -1;                            // tuning hook: PK_GEMM_SPLIT_MODE=0 (fill two waves) | 1 (least last-wave waste)
         if (mode < 0) { const char* e = getenv("PK_GEMM_SPLIT_MODE"); mode = e ? atoi(e) : 0; }   // measured: mode 0 = 91.2 ms/step, mode 1 = 94-97 (profiles/r01_notes.md)
         const int sms = num_sms();
-        if (mode == 0) {
+        if (mode == 0 || mode == 2) {
             if (out_tiles < 2 * sms) {
                 splits = (int)((2 * sms + out_tiles / 2) / out_tiles);
                 if (splits > k_iters_total / 8) splits = k_iters_total / 8;
                 if (splits > 64) splits = 64;
+                if (mode == 2 && splits >= 1 && splits + 1 <= k_iters_total / 8) {
+                    // one more split when it fills the last wave noticeably better (fc2 wgrad: 188 tiles, 2 -> 3 splits = 0.85 -> 0.95)
+                    auto eff = [&](long long sp) { const long long u = out_tiles * sp; return (double)u / (double)(((u + sms - 1) / sms) * sms); };
+                    if (eff(splits + 1) > eff(splits) + 0.05) ++splits;
+                }
             }
-        } else if (out_tiles < 6 * sms) {
+        } else if (mode == 1 && out_tiles < 6 * sms) {
             // pick the split count (<= 16, >= 8 k-iterations each) that wastes the fewest SM-slots in the last wave
             double best = 0.0;
             for (int s = 1; s <= 16 && s <= k_iters_total / 8; ++s) {

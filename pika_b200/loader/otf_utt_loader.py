@@ -104,8 +104,9 @@ def assemble(pcm, tgt, meta, args):
     B = len(pcm)
     n_max = max(max(m[0] for m in meta), max(m[3] for m in meta))
     u_max = max(len(t) for t in tgt)
-    pcm_t = torch.zeros(B, n_max, dtype=torch.int16)
-    target = torch.full((B, u_max), args.padding_tgt, dtype=torch.int32)
+    pin = torch.cuda.is_available()          # page-locked staging: the trainer's non_blocking H2D copy overlaps the previous step
+    pcm_t = torch.zeros(B, n_max, dtype=torch.int16, pin_memory=pin)
+    target = torch.full((B, u_max), args.padding_tgt, dtype=torch.int32, pin_memory=pin)
     for i in range(B):
         pcm_t[i, :meta[i][0]] = torch.from_numpy(pcm[i].copy())
         target[i, :len(tgt[i])] = torch.from_numpy(tgt[i])
