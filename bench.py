@@ -104,7 +104,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-NCU_FC2_TRAFFIC_BYTES = 17.231e9   # dram__bytes_read.sum + dram__bytes_write.sum of one fc2 launch, ncu --set full capture
+NCU_FC2_TRAFFIC_BYTES = 17.231e9       # dram__bytes_read.sum + dram__bytes_write.sum of one plain fc2 launch (profiles/r01_gemm_fc2.ncu.txt)
+NCU_FC2_LSE_TRAFFIC_BYTES = 18.768e9   # same for the launch with the row-LSE epilogue (profiles/r01_gemm_fc2_lse.ncu.txt)
 CPU_THREADS_CAP = 32      # torch-CPU fp32 layers stop scaling (and oversubscribe) beyond a few dozen threads on the 128-core hosts
 
 
@@ -398,9 +399,10 @@ def run_ours(a):
         "gpu_launches": launches,
         "roofline": {"kernel": "gemm_tcgen05_kernel (joint fc2 forward, M=%d N=%d K=%d, bias%s)" % (R, a.V, H, " + fused row-LSE epilogue" if fused_lse else ""), "bound": "tensor",
                      "achieved": g_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": g_tf / tf_burst,
-                     "traffic": NCU_FC2_TRAFFIC_BYTES if (R, a.V, H) == (1159680, 6000, 1024) else None,
-                     "traffic_source": "profiles/r01_gemm_fc2.ncu.txt (dram read 3.36 GB + write 13.88 GB per launch; algorithmic: "
-                                       "A 2.38 GB + B 0.012 GB + C 13.92 GB)",
+                     "traffic": (NCU_FC2_LSE_TRAFFIC_BYTES if fused_lse else NCU_FC2_TRAFFIC_BYTES) if (R, a.V, H) == (1159680, 6000, 1024) else None,
+                     "traffic_source": ("profiles/r01_gemm_fc2_lse.ncu.txt (dram read 4.67 GB + write 14.10 GB per launch" if fused_lse else
+                                        "profiles/r01_gemm_fc2.ncu.txt (dram read 3.36 GB + write 13.88 GB per launch") +
+                                       "; algorithmic: A 2.38 GB + B 0.012 GB + C 13.92 GB (+ 0.22 GB row partials when fused))",
                      "launch_ms": g_ms, "launch_ms_plain_epilogue": g_ms_plain},
         "roofline_loss": {"kernel": ("rnnt_rowfinish + rnnt_lattice + rnnt_grad (first pass done in the fc2 GEMM epilogue)" if fused_lse else
                                      "rnnt_rowstats + rnnt_lattice + rnnt_grad (fused log-softmax + RNN-T loss + gradient)"), "bound": "hbm",
