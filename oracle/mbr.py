@@ -1,9 +1,11 @@
 """Oracle: MBR training batch restated with torch-CPU autograd, following
 trainer/train_transducer_mbr_bmuf_otfaug.py:140-235 line by line (given an N-best list).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity status: UNPINNED against the reference itself --
-the MBR trainer is a script whose loop body depends on PyKaldi, warp_rnnt and editdistance and cannot be
-imported; its N-best input is pinned (the decoder fixtures), its arithmetic is restated here.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity status: PINNED -- the MBR trainer is a script that cannot be
+imported, so tests/golden/make_golden.py (``golden_mbr``) reads the loop-body source text from the reference, and executes
+it on CPU with the reference Net and TransducerDecoder (repairs: ``.cuda()`` -> CPU, ``editdistance.eval`` = Levenshtein,
+warp_rnnt -> torchaudio rnnt_loss); tests/test_oracle_mbr.py checks this restatement against that run: MBR loss equal,
+RNN-T loss to 3e-6, every parameter gradient to <= 2.5e-3 (norms <= 2e-4) on the high-gain decode fixture.
 """
 import numpy as np
 import torch

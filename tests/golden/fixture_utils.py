@@ -27,3 +27,14 @@ def decode_fixture_reinit(m, blank_bias=5.0, s_l=0.15, s_hh=0.04, s_j=0.05, s_o=
         m.fc2.weight.normal_(0, s_o, generator=gg)
         m.fc2.bias[0] += blank_bias
     return m
+
+
+def grad_fingerprint(g, n=384):
+    """Compact, position-sensitive summary of a gradient tensor: [sum, abs-sum, l2 norm] followed by n strided samples
+    (all elements when the tensor has at most n).  Used to pin whole-model gradients without storing 90 M floats."""
+    import numpy as np
+    f = g.detach().double().flatten()
+    step = max(1, f.numel() // n)
+    samp = f[::step][:n]
+    head = np.array([float(f.sum()), float(f.abs().sum()), float(f.norm())])
+    return np.concatenate([head, samp.numpy()])

@@ -240,9 +240,91 @@ def golden_rnnt():
     print("rnnt done")
 
 
+def golden_mbr():
+    """MBR training batch: EXECUTES the reference's own loop body (trainer/train_transducer_mbr_bmuf_otfaug.py, from the
+    '#nbest genereation' comment to 'out.backward(mbr_grad)') on CPU.  The script cannot be imported (it runs its
+    training loop inside a function that needs PyKaldi loaders, NCCL and CUDA), so the loop-body source text is read from
+    /root/reference at generation time, dedented and exec'd in a namespace that supplies what the surrounding function
+    would have: the reference Net and TransducerDecoder, an SGD optimiser, the batch, and three environment repairs --
+    ``.cuda()`` / ``torch.cuda.*Tensor`` mapped to CPU, ``editdistance.eval`` (absent package) = plain Levenshtein,
+    ``RNNTLoss.apply`` (warp_rnnt, CUDA only) = torchaudio's rnnt_loss(reduction='none').  No reference arithmetic is
+    altered.  Stores the inputs, the N-best list, both losses and a fingerprint of EVERY parameter gradient."""
+    import types
+    import textwrap
+    import torchaudio
+    from torch.autograd import Variable
+    ref_shim.load_beam_module()
+    from decoder.transducer_decoder import TransducerDecoder
+    import decoder.beam_transducer as bt
+    from fixture_utils import decode_fixture_reinit, grad_fingerprint
+    V, beam = 40, 4
+    m = build_ref_model(V)
+    disable_dropout(m)
+    decode_fixture_reinit(m)
+    d = np.load(os.path.join(HERE, "decode_small.npz"))
+    x = torch.from_numpy(d["x"])
+    tl = torch.from_numpy(d["tlens"]).int()
+    g = torch.Generator().manual_seed(11)
+    ul = torch.tensor([5, 3, 4], dtype=torch.int32)
+    target = torch.full((3, 5), V, dtype=torch.long)
+    for i in range(3):
+        target[i, :ul[i]] = torch.randint(1, V, (int(ul[i]),), generator=g)
+    args = types.SimpleNamespace(local_rank=0, rnnt_scale=0.5, sm_scale=0.8, blk=0, padding_idx=V, grad_clip=0.0,
+                                 las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None, nonblk_reward=0.0)
+    dec = TransducerDecoder(m, 3, beam, n_best=beam, blk=0, global_scorer=bt.GlobalScorer(), sm_scale=args.sm_scale,
+                            cuda=False, beam_prune=False, args=args)
+
+    def lev(a, b):
+        dd = np.zeros((len(a) + 1, len(b) + 1), dtype=np.int64)
+        dd[:, 0] = np.arange(len(a) + 1)
+        dd[0, :] = np.arange(len(b) + 1)
+        for i in range(1, len(a) + 1):
+            for j in range(1, len(b) + 1):
+                dd[i, j] = min(dd[i - 1, j] + 1, dd[i, j - 1] + 1, dd[i - 1, j - 1] + (a[i - 1] != b[j - 1]))
+        return int(dd[len(a), len(b)])
+
+    def transducer_loss(log_probs, labels, frame_lens, label_lens):
+        return torchaudio.functional.rnnt_loss(log_probs, labels.int(), frame_lens.int(), label_lens.int(), blank=0,
+                                               reduction="none", fused_log_softmax=False)
+
+    src = open(ref_shim.REF + "/trainer/train_transducer_mbr_bmuf_otfaug.py").read().split("\n")
+    i0 = next(i for i, l in enumerate(src) if "#nbest genereation" in l)
+    i1 = next(i for i, l in enumerate(src) if "out.backward(mbr_grad)" in l)
+    body = textwrap.dedent("\n".join(src[i0:i1 + 1]))
+    ns = dict(model=m, trans_decoder=dec, data_batch=x.clone(), len_batch=tl.clone(), ali_lens=ul.clone(),
+              target_batch=target.clone(), optimizer=torch.optim.SGD(m.parameters(), 1e-3), spec_augmentor=None, args=args,
+              transducer_loss=transducer_loss, beam_size=beam, F=F, torch=torch, Variable=Variable,
+              editdistance=types.SimpleNamespace(eval=lev))
+    saved = (torch.Tensor.cuda, torch.cuda.FloatTensor, torch.cuda.LongTensor)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cuda.FloatTensor, torch.cuda.LongTensor = torch.FloatTensor, torch.LongTensor
+    try:
+        exec(compile(body, "reference_mbr_loop_body", "exec"), ns)
+    finally:
+        torch.Tensor.cuda, torch.cuda.FloatTensor, torch.cuda.LongTensor = saved
+    hyps = [[[int(t) for t in h] for h in row] for row in ns["hyps"]]
+    scores = [[float(sc) for sc in row] for row in ns["scores"]]
+    L = max(len(h) for row in hyps for h in row)
+    hyp_arr = np.full((3, beam, L), -2, np.int64)
+    for i in range(3):
+        for j in range(beam):
+            hyp_arr[i, j, :len(hyps[i][j])] = hyps[i][j]
+    out = dict(target=target.numpy(), ulens=ul.numpy(), hyps=hyp_arr, scores=np.array(scores, np.float64),
+               mbr_loss=np.array(float(ns["mbr_loss"])), rnnt_loss=np.array(float(ns["rnnt_loss"])),
+               rnnt_scale=np.array(args.rnnt_scale), sm_scale=np.array(args.sm_scale))
+    n_zero = 0
+    for k, prm in m.named_parameters():
+        gr = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        n_zero += int(prm.grad is None)
+        out["g:" + k] = grad_fingerprint(gr)
+    np.savez_compressed(os.path.join(HERE, "mbr_small.npz"), **out)
+    print("mbr: loss %.6f rnnt %.6f, %d params (%d without grad), hyps lens %s" %
+          (out["mbr_loss"], out["rnnt_loss"], len([k for k in out if k.startswith("g:")]), n_zero, [len(h) for h in hyps[0]]))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rnnt", "frontend", "specaug", "encoder", "model", "decode"]
+    which = sys.argv[1:] or ["rnnt", "frontend", "specaug", "encoder", "model", "decode", "mbr"]
     table = dict(rnnt=golden_rnnt, frontend=golden_frontend, specaug=golden_specaug,
-                 encoder=golden_encoder_eval, model=golden_model, decode=golden_decode)
+                 encoder=golden_encoder_eval, model=golden_model, decode=golden_decode, mbr=golden_mbr)
     for w in which:
         table[w]()
