@@ -11,10 +11,12 @@ layers, a small C file for the lattice DP at larger sizes) and cites the
 reference ``file:line`` it follows (paths relative to ``/root/reference``).
 
 Pinning status (see DESIGN.md "Oracle"):
-  * model / joint / decoder / SpecAugment / BMUF update: pinned against the
-    reference's own Python modules executed in the build container
-    (``tests/golden/make_golden.py`` imports them from ``/root/reference`` and
-    commits the outputs as ``tests/golden/*.npz``).
+  * model / joint / decoder / SpecAugment / BMUF update / MBR batch: pinned against
+    the reference's own Python executed in the build container
+    (``tests/golden/make_golden.py`` imports the modules from ``/root/reference`` --
+    for the MBR trainer, which is a script, it executes the loop-body source text;
+    for BMUF it runs the reference BmufTrainer on two gloo ranks -- and commits the
+    outputs as ``tests/golden/*.npz``).
   * RNN-T loss: the reference delegates to the un-vendored, un-pinned
     ``warp_rnnt`` package (README.md:34-36).  Pinned against
     ``torchaudio.functional.rnnt_loss`` (an independent implementation of the

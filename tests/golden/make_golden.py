@@ -240,6 +240,50 @@ def golden_rnnt():
     print("rnnt done")
 
 
+def _bmuf_ref_worker(rank, world, port, q):
+    """one gloo rank running the REFERENCE trainer/bmuf.py:BmufTrainer (repairs: backend nccl -> gloo, .cuda() -> CPU)"""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    ref_shim.install()
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend=None, **kw: real_init(backend="gloo", **kw)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    from trainer.bmuf import BmufTrainer, SUCCESS
+    torch.manual_seed(100 + rank)
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+    tr = BmufTrainer(0, rank, world, model, 0.9, 1.0)
+    out = [tr.param.clone().numpy()]
+    for it in range(3):
+        g = torch.Generator().manual_seed(7 * it + rank)
+        with torch.no_grad():
+            vec = torch.nn.utils.parameters_to_vector(model.parameters())
+            vec = vec + 0.01 * torch.randn(vec.shape, generator=g)
+            torch.nn.utils.vector_to_parameters(vec, model.parameters())
+        assert tr.update_and_sync() == SUCCESS
+        out.append(tr.param.clone().numpy())
+    q.put((rank, np.stack(out), torch.nn.utils.parameters_to_vector(model.parameters()).detach().numpy()))
+    dist.destroy_process_group()
+
+
+def golden_bmuf():
+    """Reference BmufTrainer on 2 gloo ranks: the parameter vector after the initial broadcast and after each of three
+    block syncs with rank-specific local updates (same seeds as tests/test_bmuf_gloo_cpu.py)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_bmuf_ref_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(30)
+    # every rank ends each sync with the same parameters (broadcast), and the model holds them
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[0][1][-1]) and np.array_equal(res[1][2], res[0][1][-1])
+    np.savez_compressed(os.path.join(HERE, "bmuf_2rank.npz"), params=res[0][1])
+    print("bmuf: params", res[0][1].shape, "first", res[0][1][:, 0])
+
+
 def golden_mbr():
     """MBR training batch: EXECUTES the reference's own loop body (trainer/train_transducer_mbr_bmuf_otfaug.py, from the
     '#nbest genereation' comment to 'out.backward(mbr_grad)') on CPU.  The script cannot be imported (it runs its
@@ -323,8 +367,8 @@ def golden_mbr():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rnnt", "frontend", "specaug", "encoder", "model", "decode", "mbr"]
+    which = sys.argv[1:] or ["rnnt", "frontend", "specaug", "encoder", "model", "decode", "mbr", "bmuf"]
     table = dict(rnnt=golden_rnnt, frontend=golden_frontend, specaug=golden_specaug,
-                 encoder=golden_encoder_eval, model=golden_model, decode=golden_decode, mbr=golden_mbr)
+                 encoder=golden_encoder_eval, model=golden_model, decode=golden_decode, mbr=golden_mbr, bmuf=golden_bmuf)
     for w in which:
         table[w]()

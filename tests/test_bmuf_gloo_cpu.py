@@ -1,6 +1,7 @@
 """BMUF protocol across 2 ranks on CPU (gloo): the drop-in BmufTrainer's collective sequence
 (initial broadcast, all-reduce of the block delta, replicated block-momentum update, collective NaN stop,
-sum_reduce/broadcast helpers) against the oracle of trainer/bmuf.py:76-100.  The element-wise kernels are
+sum_reduce/broadcast helpers) against the oracle of trainer/bmuf.py:76-100 AND against the parameter trajectory of the
+reference's own BmufTrainer run on 2 gloo ranks in the build container (tests/golden/bmuf_2rank.npz, make_golden.py:golden_bmuf).  The element-wise kernels are
 CUDA-only, so this host-logic test injects numpy implementations of the three ops (oracle/train.py)."""
 import os
 import sys
@@ -53,15 +54,25 @@ def worker(rank, world, port, q):
     glob = flat0.numpy().astype(np.float64).copy()
     dprev = np.zeros_like(glob)
     ok = True
-    for it in range(2):
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "bmuf_2rank.npz"))["params"]      # [1 + syncs, n] reference trajectory
+    pvec = lambda: torch.nn.utils.parameters_to_vector(model.parameters()).detach().numpy()   # noqa: E731  (flat buffer minus alignment padding)
+    ok &= np.array_equal(pvec(), gold[0])                                                 # rank 0's initial weights everywhere
+    for it in range(3):
         g = torch.Generator().manual_seed(7 * it + rank)
         with torch.no_grad():
-            tr.flat.data.add_(0.01 * torch.randn(tr.flat.data.shape, generator=g))
+            noise = 0.01 * torch.randn(gold.shape[1], generator=g)          # same draw as the reference run: one value per parameter
+            off = 0
+            for prm in model.parameters():                                  # in place: parameters are views of the flat buffer
+                prm.add_(noise[off:off + prm.numel()].view_as(prm))
+                off += prm.numel()
         locals_ = [torch.zeros_like(flat0) for _ in range(world)]
         dist.all_gather(locals_, tr.flat.data.clone())
         assert tr.update_and_sync() == SUCCESS
         glob, dprev = ot.bmuf_update(glob, [l.numpy().astype(np.float64) for l in locals_], dprev, bm, blr)
         ok &= np.allclose(tr.param.numpy(), glob, atol=1e-6) and torch.equal(tr.param, tr.flat.data)
+        # reference: reduce to rank 0 -> update -> broadcast; here: all-reduce -> replicated update.  Same fp32 formula; the only
+        # difference is gloo's summation order over 2 ranks (commutative), so the trajectories agree to the last few ulps
+        ok &= np.allclose(pvec(), gold[it + 1], rtol=0, atol=2e-7)
     # helper collectives
     t = torch.tensor([float(rank + 1), 10.0])
     tr.sum_reduce(t)
