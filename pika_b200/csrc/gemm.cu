@@ -129,6 +129,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 const int zb1 = z / p.zb0, zb0 = z - zb1 * p.zb0;
                 const int m0 = mb * BM, n0 = nb * BN;
                 const int i0 = split * p.iters_per_split, i1 = min(k_iters_total, i0 + p.iters_per_split);
+                if (p.n_pairs == 1 && p.kz_count == 1) {
+                    // One (A, B) pair and no batched reduction (every forward / dgrad / plain wgrad GEMM): the flattened index IS the
+                    // k-block and the selectors are tile constants.  The general loop below spends ~160 SASS instructions per k-block
+                    // in this single thread (two integer divisions, four selector ladders) -- more than the 4 MMAs of a stage take --
+                    // so the common case gets a loop that only waits, arms the barrier and issues the two TMA loads.
+                    const int a2 = pick_sel(p.a_sel2, zb0, zb1, 0), a3 = pick_sel(p.a_sel3, zb0, zb1, 0);
+                    const int b2 = pick_sel(p.b_sel2, zb0, zb1, 0), b3 = pick_sel(p.b_sel3, zb0, zb1, 0);
+                    const int a_off = p.a_off[0], b_off = p.b_off[0];
+                    for (int kb = i0; kb < i1; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                        uint8_t* sb = sa + A_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        if (A_MN) {
+#pragma unroll
+                            for (int c = 0; c < BM / 64; ++c)
+                                tma_load_4d(sa + c * (64 * BK * 2), &p.a[0], &full_bar[stage], m0 + c * 64, kb * BK + a_off, a2, a3);
+                        } else {
+                            tma_load_4d(sa, &p.a[0], &full_bar[stage], kb * BK, m0 + a_off, a2, a3);
+                        }
+                        if (B_MN) {
+#pragma unroll
+                            for (int c = 0; c < BN / 64; ++c)
+                                tma_load_4d(sb + c * (64 * BK * 2), &p.b[0], &full_bar[stage], n0 + c * 64, kb * BK + b_off, b2, b3);
+                        } else {
+                            tma_load_4d(sb, &p.b[0], &full_bar[stage], kb * BK, n0 + b_off, b2, b3);
+                        }
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    continue;
+                }
                 for (int i = i0; i < i1; ++i) {
                     const int pr = i / kzb;
                     const int rem = i - pr * kzb;
