@@ -109,8 +109,11 @@ int pk_gemm_bf16(const pk_gemm_desc* desc, void* stream);
  *           Entries of padded nodes and of the row padding [V, ldv) are written as 0.
  *   dlogits_colsum [ldv] f32 or NULL: sum of dlogits over all (b,t,u) rows = the joint fc2 bias gradient,
  *           produced by the gradient pass itself (each thread owns fixed columns), so dlogits is not re-read.
+ *           Deterministic: per-CTA partial rows are added in a fixed order (no atomics); when requested the workspace
+ *           must hold pk_rnnt_loss_workspace_bytes + pk_rnnt_loss_colsum_workspace_bytes bytes.
  */
 long long pk_rnnt_loss_workspace_bytes(int B, int T, int U1);
+long long pk_rnnt_loss_colsum_workspace_bytes(int B, int T, int U1, int ldv);
 int pk_rnnt_loss_fwd_bwd(const void* logits, int dtype, const int* labels, const int* frame_lens,
                          const int* label_lens, int B, int T, int U1, int V, int ldv, int ld_labels,
                          const float* grad_scale, float* costs, void* dlogits, float* dlogits_colsum, void* workspace,
@@ -203,8 +206,9 @@ int pk_embedding_bwd(const long long* idx, const void* dout, int dtype, int ld, 
  *                                     ranks between the two is an NCCL all-reduce issued by the host side.
  */
 int pk_absmax(const float* x, long long n, float* out, int* nan_flag, void* stream);
+/* nan_flag (may be NULL): the flag pk_absmax raised; when set the clip coefficient is NaN, as torch's clip_grad_norm_(inf) gives */
 int pk_sgd_nesterov_clip(float* p, const float* g, float* buf, long long n, float lr, float momentum, float max_norm,
-                         const float* absmax, int first, void* stream);
+                         const float* absmax, const int* nan_flag, int first, void* stream);
 int pk_bmuf_delta(const float* glob, const float* local, float* delta, long long n, void* stream);
 int pk_bmuf_update(float* glob, float* local, float* delta_prev, const float* delta_sum, long long n, int world,
                    float block_momentum, float block_lr, void* stream);

@@ -25,21 +25,25 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
         bad |= !(x[i] == x[i]);
     }
     m = warp_max(m);
+    const bool warp_bad = __any_sync(0xffffffffu, bad);          // all 32 lanes reach this point
     if ((threadIdx.x & 31) == 0) {
         atomicMax(out_bits, __float_as_uint(m));     // non-negative floats order like their bit patterns
-        if (nan_flag && __any_sync(0xffffffffu, bad)) atomicExch(nan_flag, 1);
+        if (nan_flag && warp_bad) atomicExch(nan_flag, 1);
     }
-    if (nan_flag && bad) atomicExch(nan_flag, 1);
 }
 
 // g' = g * min(1, max_norm / (absmax + 1e-6));  buf = first ? g' : mom*buf + g';  p -= lr * (g' + mom*buf)
 __global__ void __launch_bounds__(256) sgd_nesterov_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
                                                            long long n, float lr, float mom, float max_norm,
-                                                           const unsigned int* __restrict__ absmax_bits, int first) {
+                                                           const unsigned int* __restrict__ absmax_bits,
+                                                           const int* __restrict__ nan_flag, int first) {
     float coef = 1.f;
     if (max_norm > 0.f && absmax_bits) {
         const float tot = __uint_as_float(*absmax_bits);
         coef = fminf(1.f, max_norm / (tot + 1e-6f));
+        // fmaxf drops NaNs, torch.max does not: clip_grad_norm_(inf) of a gradient holding a NaN gives a NaN coefficient,
+        // i.e. every parameter turns NaN (and the next BMUF sync stops the run); reproduced through the flag absmax raised
+        if (nan_flag && *nan_flag) coef = __int_as_float(0x7fc00000);
     }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gi = g[i] * coef;
@@ -85,9 +89,9 @@ extern "C" int pk_absmax(const float* x, long long n, float* out, int* nan_flag,
     return 0;
 }
 extern "C" int pk_sgd_nesterov_clip(float* p, const float* g, float* buf, long long n, float lr, float momentum, float max_norm,
-                                    const float* absmax, int first, void* stream) {
+                                    const float* absmax, const int* nan_flag, int first, void* stream) {
     sgd_nesterov_kernel<<<og(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, buf, n, lr, momentum, max_norm,
-                                                                                 reinterpret_cast<const unsigned int*>(absmax), first);
+                                                                                 reinterpret_cast<const unsigned int*>(absmax), nan_flag, first);
     PK_CHECK_LAUNCH(); count_launch();
     return 0;
 }

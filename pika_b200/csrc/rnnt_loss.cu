@@ -440,15 +440,32 @@ __global__ void __launch_bounds__(GRAD_THREADS, MINB) rnnt_grad_kernel(const T* 
         }
     }
     if (colsum) {
+        // one partial row per CTA (no atomics): colsum_partials_kernel adds them in a fixed order, so the fc2 bias
+        // gradient is bit-reproducible from run to run
+        float* part = colsum + (size_t)blockIdx.x * d.ldv;
 #pragma unroll
         for (int gq = 0; gq < GRAD_MAXG; ++gq) {
             const int i = tid + gq * GRAD_THREADS;
             if (i < nvec_ld) {
 #pragma unroll
-                for (int e = 0; e < VN; ++e) atomicAdd(&colsum[i * VN + e], cs[gq][e]);
+                for (int e = 0; e < VN; ++e) part[i * VN + e] = cs[gq][e];
             }
         }
     }
+}
+
+// out[c] = sum over the n_part partial rows, in index order (4 independent chains per thread for latency, fixed association)
+__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ part, int n_part, int ld, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ld) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int i = 0;
+    for (; i + 4 <= n_part; i += 4) {
+        a0 += part[(size_t)(i + 0) * ld + c]; a1 += part[(size_t)(i + 1) * ld + c];
+        a2 += part[(size_t)(i + 2) * ld + c]; a3 += part[(size_t)(i + 3) * ld + c];
+    }
+    for (; i < n_part; ++i) a0 += part[(size_t)i * ld + c];
+    out[c] = (a0 + a1) + (a2 + a3);
 }
 
 }  // namespace pk
@@ -458,6 +475,23 @@ extern "C" long long pk_rnnt_loss_workspace_bytes(int B, int T, int U1) {
     const long long skew = (long long)B * nd * U1;
     const long long nodes = (long long)B * T * U1;
     return (2 * skew + 3 * nodes) * 4 + 2 * skew * 8 + 256;
+}
+// gradient-kernel grid: shared by the launch and by the column-sum workspace query
+static void rnnt_grad_grid(long long rows, int* ru_out, int* ctas_per_sm_out, long long* rpc_out, int* ggrid_out, int* variant_out) {
+    static int variant = -1;                         // tuning hook (PK_RNNT_GRAD_VARIANT=0..3), default chosen by measurement
+    if (variant < 0) { const char* e = getenv("PK_RNNT_GRAD_VARIANT"); variant = e ? atoi(e) : 1; }
+    const int ru = (variant == 0) ? 1 : (variant == 3 ? 4 : 2);
+    const int ctas_per_sm = (variant == 2) ? 2 : 3;
+    const int gcta = pk::num_sms() * ctas_per_sm * 4;
+    long long rpc = (rows + gcta - 1) / gcta;
+    rpc = (rpc + ru - 1) / ru * ru;
+    if (rpc > 2048) rpc = 2048;                      // 16 bytes of shared memory per row
+    *ru_out = ru; *ctas_per_sm_out = ctas_per_sm; *rpc_out = rpc; *ggrid_out = (int)((rows + rpc - 1) / rpc); *variant_out = variant;
+}
+extern "C" long long pk_rnnt_loss_colsum_workspace_bytes(int B, int T, int U1, int ldv) {
+    int ru, cps, ggrid, variant; long long rpc;
+    rnnt_grad_grid((long long)B * T * U1, &ru, &cps, &rpc, &ggrid, &variant);
+    return (long long)ggrid * ldv * 4;
 }
 
 static int rnnt_loss_impl(const void* logits, int dtype, const int* labels, const int* frame_lens,
@@ -512,20 +546,20 @@ static int rnnt_loss_impl(const void* logits, int dtype, const int* labels, cons
     PK_CHECK_LAUNCH(); count_launch();
     if (dlogits != nullptr) {
         PK_CHECK_ARG(ldv / vn <= GRAD_THREADS * GRAD_MAXG, "V too large for the gradient kernel (V <= 8192 bf16 / 4096 f32)");
-        if (dlogits_colsum) PK_CHECK_CUDA(cudaMemsetAsync(dlogits_colsum, 0, sizeof(float) * ldv, stream));
-        static int variant = -1;                         // tuning hook (PK_RNNT_GRAD_VARIANT=0..3), default chosen by measurement
-        if (variant < 0) { const char* e = getenv("PK_RNNT_GRAD_VARIANT"); variant = e ? atoi(e) : 1; }
-        const int ru = (variant == 0) ? 1 : (variant == 3 ? 4 : 2);
-        const int ctas_per_sm = (variant == 2) ? 2 : 3;
-        const int gcta = num_sms() * ctas_per_sm * 4;
-        long long rpc = (rows + gcta - 1) / gcta;
-        rpc = (rpc + ru - 1) / ru * ru;
-        if (rpc > 2048) rpc = 2048;                      // 16 bytes of shared memory per row
-        const int ggrid = (int)((rows + rpc - 1) / rpc);
+        int ru, ctas_per_sm, ggrid, variant; long long rpc;
+        rnnt_grad_grid(rows, &ru, &ctas_per_sm, &rpc, &ggrid, &variant);
+        (void)ru; (void)ctas_per_sm;
+        float* cs_part = nullptr;                        // [ggrid][ldv] per-CTA partial column sums, after the lattice workspace
+        if (dlogits_colsum) {
+            const long long base_bytes = pk_rnnt_loss_workspace_bytes(B, T, U1);
+            PK_CHECK_ARG(workspace_bytes >= base_bytes + (long long)ggrid * ldv * 4,
+                         "workspace too small for the column sums (add pk_rnnt_loss_colsum_workspace_bytes)");
+            cs_part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + base_bytes);
+        }
         const size_t gsmem = (size_t)rpc * 16;
 #define PK_GRAD_LAUNCH(TT, RU, MB)                                                                                         \
         rnnt_grad_kernel<TT, RU, MB><<<ggrid, GRAD_THREADS, gsmem, stream>>>(reinterpret_cast<const TT*>(logits), labels, label_lens, d, lse, \
-                                                                            gb, gl, reinterpret_cast<TT*>(dlogits), dlogits_colsum, rpc)
+                                                                            gb, gl, reinterpret_cast<TT*>(dlogits), cs_part, rpc)
         if (dtype == PK_BF16) {
             if (variant == 0) PK_GRAD_LAUNCH(__nv_bfloat16, 1, 3);
             else if (variant == 2) PK_GRAD_LAUNCH(__nv_bfloat16, 2, 2);
@@ -536,6 +570,10 @@ static int rnnt_loss_impl(const void* logits, int dtype, const int* labels, cons
         }
 #undef PK_GRAD_LAUNCH
         PK_CHECK_LAUNCH(); count_launch();
+        if (dlogits_colsum) {
+            colsum_partials_kernel<<<(ldv + 255) / 256, 256, 0, stream>>>(cs_part, ggrid, ldv, dlogits_colsum);
+            PK_CHECK_LAUNCH(); count_launch();
+        }
     }
     return 0;
 }

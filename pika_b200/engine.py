@@ -667,29 +667,64 @@ class JointFn(torch.autograd.Function):
         return d_enc, d_pred, None
 
 
+_UNIT_LOSS_GRAD = False
+
+
+def assume_unit_loss_grad(flag):
+    """The training step calls ``costs.sum().backward()`` (trainer/train_transducer_bmuf_otfaug.py:97-103), i.e. the upstream
+    gradient of every cost is exactly 1.  TrainStep declares that here so JointLossFn.backward does no re-scaling work;
+    any other caller gets the general (scaled) backward."""
+    global _UNIT_LOSS_GRAD
+    _UNIT_LOSS_GRAD = bool(flag)
+
+
 class JointLossFn(torch.autograd.Function):
     """Fused joint + log-softmax + RNN-T loss: the logits tensor is produced, consumed by the loss
     kernels and overwritten IN PLACE by d(loss)/d(logits); the joint backward then runs immediately, so
-    only one [B,T,U1,V] tensor ever exists.  Returns costs [B]; upstream gradients must be uniform
-    (``.sum()`` / a scalar multiple), as in trainer/train_transducer_bmuf_otfaug.py:97-99."""
+    only one [B,T,U1,V] tensor ever exists.  Returns costs [B].
+
+    Gradient contract (one place): every Function of this engine OVERWRITES the ``.grad`` of the parameters it owns
+    (EmbeddingFn zero-fills, then scatters), so one forward + one backward per ``zero_grad`` is the supported pattern, as in
+    the reference loop (:74, :103).  The joint's parameter gradients are produced here in forward for an upstream gradient
+    of 1 per utterance; ``backward`` re-scales them (and d_enc / d_pred) when the upstream gradient is a different UNIFORM
+    scalar, and scales d_enc / d_pred per utterance otherwise -- per-utterance weights on the joint's OWN parameters are not
+    representable after the fact and raise.  With grad mode off (``need_grad`` False: the eval branch of run_one_epoch) only the
+    costs are computed and no gradient buffer is touched."""
 
     @staticmethod
-    def forward(ctx, enc, pred, model, labels, frame_lens, label_lens):
+    def forward(ctx, enc, pred, model, labels, frame_lens, label_lens, need_grad=True):
         logits, st = _joint_forward(enc, pred, model, want_lse=True)
         V = st["dims"][4]
+        ctx.need_grad = need_grad
+        if not need_grad:
+            costs, _ = K.rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=V, want_grad=False, row_lse=st.pop("row_lse"))
+            return costs
         db2 = torch.empty(logits.shape[-1], dtype=torch.float32, device=logits.device)
         costs, _ = K.rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=V, dlogits=logits, colsum=db2,
                                        row_lse=st.pop("row_lse"))
         d_enc, d_pred = _joint_backward(logits, st, model, db2=db2)
         del logits, st
         ctx.save_for_backward(d_enc, d_pred)
+        ctx.model = model
         return costs
 
     @staticmethod
     def backward(ctx, dcosts):
+        if not ctx.need_grad:
+            raise RuntimeError("JointLossFn: forward ran with grad mode off; there is nothing to back-propagate")
         d_enc, d_pred = ctx.saved_tensors
-        # uniform upstream gradient (1 for .sum()); parameter grads of the joint were written for scale 1
-        return d_enc, d_pred, None, None, None, None
+        if not _UNIT_LOSS_GRAD:
+            w = dcosts.detach().float()
+            if not bool((w == w[0]).all()):
+                raise RuntimeError("JointLossFn: per-utterance loss weights are not supported by the fused joint backward "
+                                   "(its parameter gradients were formed for a uniform upstream gradient)")
+            if float(w[0]) != 1.0:
+                m = ctx.model
+                for p in (m.fc1.weight, m.fc1.bias, m.fc_gate.weight, m.fc_gate.bias, m.fc2.weight, m.fc2.bias):
+                    p.grad.mul_(w[0])
+                d_enc = d_enc * w[0].to(d_enc.dtype)
+                d_pred = d_pred * w[0].to(d_pred.dtype)
+        return d_enc, d_pred, None, None, None, None, None
 
 
 class RNNTLossFn(torch.autograd.Function):
@@ -824,4 +859,5 @@ def transducer_loss(model, x, y, frame_lens, label_lens):
     """Fused training path: costs [B] with gradients wired to every parameter."""
     enc = encoder_forward_act(model.encoder, x)
     pred = prednet_forward_act(model, y)
-    return JointLossFn.apply(enc, pred, model, y.int().contiguous(), frame_lens.int().contiguous(), label_lens.int().contiguous())
+    return JointLossFn.apply(enc, pred, model, y.int().contiguous(), frame_lens.int().contiguous(), label_lens.int().contiguous(),
+                             torch.is_grad_enabled())

@@ -108,6 +108,8 @@ def rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=None, grad_scale
     assert logits.is_contiguous() and labels.dtype == torch.int32 and labels.dim() == 2
     assert frame_lens.dtype == torch.int32 and label_lens.dtype == torch.int32
     ws_bytes = int(lib.pk_rnnt_loss_workspace_bytes(B, T, U1))
+    if colsum is not None:
+        ws_bytes += int(lib.pk_rnnt_loss_colsum_workspace_bytes(B, T, U1, ldv))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=logits.device)
     costs = torch.empty(B, dtype=torch.float32, device=logits.device)
     if want_grad and dlogits is None:
@@ -288,9 +290,9 @@ def absmax(x, out, nan_flag=None):
     check(lib.pk_absmax(_P(x), _L(x.numel()), _P(out), _P(nan_flag), _stream()), "pk_absmax")
 
 
-def sgd_nesterov_clip(p, g, buf, lr, momentum, max_norm, absmax_t, first):
+def sgd_nesterov_clip(p, g, buf, lr, momentum, max_norm, absmax_t, first, nan_flag=None):
     check(lib.pk_sgd_nesterov_clip(_P(p), _P(g), _P(buf), _L(p.numel()), _F(lr), _F(momentum), _F(max_norm), _P(absmax_t),
-                                   _I(int(first)), _stream()), "pk_sgd_nesterov_clip")
+                                   _P(nan_flag), _I(int(first)), _stream()), "pk_sgd_nesterov_clip")
 
 
 def bmuf_delta(glob, local, delta):

@@ -64,8 +64,10 @@ class SgdNesterovClip:
     def step(self):
         f = self.flat
         if self.max_norm > 0:
+            self.nan_flag.zero_()
             K.absmax(f.grad, self.absmax, self.nan_flag)
         K.sgd_nesterov_clip(f.data, f.grad, self.buf, self.lr, self.momentum, self.max_norm,
-                            self.absmax if self.max_norm > 0 else None, self.first)
+                            self.absmax if self.max_norm > 0 else None, self.first,
+                            nan_flag=self.nan_flag if self.max_norm > 0 else None)
         self.first = False
         engine.invalidate_weights()

@@ -62,7 +62,10 @@ def run_one_epoch(epoch, model, log_f, args, bmuf_trainer, training):
         else:                                                 # empty batch (:100-101)
             loss = 0.0
             if training:
-                step.num_done += 1
+                try:
+                    step.skip()                               # still counts, still syncs (:112-123)
+                except FloatingPointError:
+                    return float('nan')
         labels = int(ali_lens_cpu.sum().item())
         loss_logger.update_and_log(labels, [loss])
     if training and bmuf_trainer.update_and_sync() != 1:

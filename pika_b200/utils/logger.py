@@ -1,42 +1,53 @@
-"""Running-loss logger -- same interface and log format as utils/logger.py (reference): per-N-labels
-running loss and 'fps' (label tokens per second, in thousands), plus an epoch summary."""
+"""Running-loss log lines for the training driver.
+
+Public contract (what the trainer script calls, and what log-scraping tools of the reference recipe parse):
+``Logger(file, every_n_labels, tags[, divisors])``, ``update_and_log(n_labels, [loss per tag])``,
+``summarize_and_log() -> (sum of the first loss, total labels)``; a window line reads
+``<tag>: <avg> \\t...fps: <k labels/s> k`` and the epoch line ``Finished, Overall Avg <tag>: <avg>\\t...Avg fps:<..> k``.
+The bookkeeping is two accumulators (window, epoch) instead of parallel lists.
+"""
 import time
 
 
+class _Acc:
+    """label count + per-tag loss sums since ``t0``"""
+
+    def __init__(self, k):
+        self.clear(k)
+
+    def clear(self, k):
+        self.labels, self.sums, self.t0 = 0, [0.0] * k, time.time()
+
+    def add(self, n, losses):
+        self.labels += n
+        self.sums = [s + float(l) for s, l in zip(self.sums, losses)]
+
+    def averages(self, div):
+        return [s / d / float(self.labels) for s, d in zip(self.sums, div)]
+
+    def rate_k(self):
+        return self.labels / (time.time() - self.t0) / 1000
+
+
 class Logger(object):
-    def __init__(self, log_file, log_per_nframes, tags, loss_per_frame=[1.0]):
-        self.log_file = log_file
-        self.num_frames = 0
-        self.total_frames = 0
-        self.loss = [0.0 for _ in tags]
-        self.total_loss = [0.0 for _ in tags]
-        self.log_per_nframes = log_per_nframes
-        self.tags = tags
-        if len(self.total_loss) != len(loss_per_frame):
-            loss_per_frame = [1.0] * len(self.total_loss)
-        self.loss_per_frame = loss_per_frame
-        self.start_time = time.time()
-        self.log_time = time.time()
+    def __init__(self, log_file, log_per_nframes, tags, loss_per_frame=(1.0,)):
+        self.log_file, self.log_per_nframes, self.tags = log_file, log_per_nframes, list(tags)
+        k = len(self.tags)
+        self.loss_per_frame = list(loss_per_frame) if len(loss_per_frame) == k else [1.0] * k
+        self._window, self._epoch = _Acc(k), _Acc(k)
 
     def update_and_log(self, num_frames, loss):
-        self.num_frames += num_frames
-        self.total_frames += num_frames
-        for i, l in enumerate(loss):
-            self.loss[i] += l
-            self.total_loss[i] += l
-        if self.num_frames >= self.log_per_nframes:
-            elapsed = time.time() - self.log_time
-            for i, l in enumerate(self.loss):
-                self.log_file.write('{}: {:.3f} \t'.format(self.tags[i], l / self.loss_per_frame[i] / float(self.num_frames)))
-            self.log_file.write('fps: {:.6f} k\n'.format(self.num_frames / elapsed / 1000))
-            self.log_file.flush()
-            self.num_frames = 0
-            self.loss = [0.0 for _ in self.tags]
-            self.log_time = time.time()
+        self._window.add(num_frames, loss)
+        self._epoch.add(num_frames, loss)
+        if self._window.labels < self.log_per_nframes:
+            return
+        cells = ''.join('{}: {:.3f} \t'.format(t, a) for t, a in zip(self.tags, self._window.averages(self.loss_per_frame)))
+        self.log_file.write(cells + 'fps: {:.6f} k\n'.format(self._window.rate_k()))
+        self.log_file.flush()
+        self._window.clear(len(self.tags))
 
     def summarize_and_log(self):
-        for i, l in enumerate(self.total_loss):
-            self.log_file.write('Finished, Overall Avg {}: {:.3f}\t'.format(self.tags[i], l / self.loss_per_frame[i] / float(self.total_frames)))
-        elapsed = time.time() - self.start_time
-        self.log_file.write('Avg fps:{:.6f} k\n'.format(self.total_frames / elapsed / 1000))
-        return self.total_loss[0], self.total_frames
+        cells = ''.join('Finished, Overall Avg {}: {:.3f}\t'.format(t, a)
+                        for t, a in zip(self.tags, self._epoch.averages(self.loss_per_frame)))
+        self.log_file.write(cells + 'Avg fps:{:.6f} k\n'.format(self._epoch.rate_k()))
+        return self._epoch.sums[0], self._epoch.labels

@@ -105,12 +105,82 @@ def golden_model():
         gr = p.grad
         out["g_" + k] = np.concatenate([[gr.double().norm().item(), gr.double().abs().max().item()],
                                         gr.flatten()[:6].double().numpy()])
+        from fixture_utils import grad_fingerprint
+        out["gs_" + k] = grad_fingerprint(gr, 512)      # [sum, abs-sum, norm] + <= 512 strided samples: pins the DIRECTION, not just the norm
     # BatchNorm running stats after one train-mode forward
     for k, v in m.state_dict().items():
         if "running" in k:
             out["bn_" + k] = np.array([v.double().sum().item(), float(v.flatten()[0])])
     np.savez_compressed(os.path.join(HERE, "model_small.npz"), **out)
     print("model_small: costs", costs.tolist(), "enc", tuple(enc.shape), "logits", tuple(logits.shape))
+
+
+from make_inputs import decode_big_inputs, full_shape_inputs  # noqa: E402  (shared with the GPU tests)
+
+
+def golden_model_full():
+    """The reference model at the BASELINE shape: T=1000 frames (T'=240), U=150, V=6000, B=2 with ragged lengths.
+    Forward + torchaudio-loss backward on the CPU (about 10 GB, a few minutes); stores strided samples only."""
+    import torchaudio
+    from fixture_utils import grad_fingerprint
+    V = 6000
+    x_np, y_np, lens_np, ulens_np = full_shape_inputs(V=V)
+    m = build_ref_model(V)
+    m.train()
+    disable_dropout(m)
+    x, y = torch.from_numpy(x_np), torch.from_numpy(y_np)
+    lens, ulens = torch.from_numpy(lens_np), torch.from_numpy(ulens_np)
+    enc, pred, logits = ref_forward_cpu(m, x, y, softmax=False)
+    logits.retain_grad()
+    lp = F.log_softmax(logits, -1)
+    tl = lens - 42
+    tl = tl // 4 + (tl % 4 != 0).int()
+    costs = torchaudio.functional.rnnt_loss(lp, y.int(), tl, ulens, blank=0, reduction="none", fused_log_softmax=False)
+    costs.sum().backward()
+    dl = logits.grad
+    out = dict(seed=np.array(2025), tlens=tl.numpy(), costs=costs.detach().numpy(), V=np.array(V),
+               enc=enc.detach()[:, ::5, ::7].contiguous().numpy(), pred=pred.detach()[:, ::3, ::7].contiguous().numpy(),
+               logits=logits.detach()[:, ::9, ::7, ::53].contiguous().numpy(),
+               lse=torch.logsumexp(logits.detach(), -1)[:, ::9, ::7].contiguous().numpy(),
+               dlogits=dl[:, ::9, ::7, ::53].contiguous().numpy(),
+               dlogits_blank=dl[:, ::3, ::3, 0].contiguous().numpy(),
+               dlogits_colsum=dl.double().sum((0, 1, 2)).numpy())
+    for k, p in m.named_parameters():
+        out["gs_" + k] = grad_fingerprint(p.grad, 256)
+    np.savez_compressed(os.path.join(HERE, "model_full_shape.npz"), **out)
+    print("model_full_shape: costs", costs.tolist(), "logits", tuple(logits.shape))
+
+
+def golden_decode_big():
+    """Reference decode_batch at the width of BASELINE config 5: beam 16, V=6000 (batch / frames reduced so the fixture
+    generates in minutes on the CPU); inputs are regenerated from the seed by the test."""
+    import types
+    ref_shim.load_beam_module()
+    from decoder.transducer_decoder import TransducerDecoder
+    import decoder.beam_transducer as bt
+    from fixture_utils import decode_fixture_reinit
+    V, B, T, beam, nbest = 6000, 6, 330, 16, 4
+    m = build_ref_model(V)
+    m.eval()
+    decode_fixture_reinit(m)
+    x = torch.from_numpy(decode_big_inputs(606, B, T))
+    frames = torch.tensor([330, 330, 301, 280, 222, 175])
+    tl = frames - 42
+    tl = tl // 4 + (tl % 4 != 0).long()
+    dargs = types.SimpleNamespace(las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None, nonblk_reward=0.0)
+    dec = TransducerDecoder(m, B, beam, n_best=nbest, blk=0, global_scorer=bt.GlobalScorer(), sm_scale=1.0, cuda=False,
+                            beam_prune=True, args=dargs)
+    with torch.no_grad():
+        ret, enc = dec.decode_batch(x, tl, max_len=[int(t) + 100 for t in tl])
+    cases = {}
+    for b in range(B):
+        for n in range(nbest):
+            cases["pred_%d_%d" % (b, n)] = np.array([int(t) for t in ret["predictions"][b][n]], np.int64)
+            cases["score_%d_%d" % (b, n)] = np.array(float(ret["scores"][b][n]))
+    print("decode_big", [len(cases["pred_%d_0" % b]) for b in range(B)], [float(ret["scores"][b][0]) for b in range(B)],
+          "distinct tokens in best hyps:", len(set(int(t) for b in range(B) for t in cases["pred_%d_0" % b])))
+    np.savez_compressed(os.path.join(HERE, "decode_big.npz"), seed=np.array(606), tlens=tl.numpy(), frames=frames.numpy(),
+                        enc=enc.numpy()[:, ::3, ::17], dims=np.array([V, B, T, beam, nbest]), **cases)
 
 
 def golden_encoder_eval():
@@ -369,6 +439,7 @@ def golden_mbr():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["rnnt", "frontend", "specaug", "encoder", "model", "decode", "mbr", "bmuf"]
     table = dict(rnnt=golden_rnnt, frontend=golden_frontend, specaug=golden_specaug,
-                 encoder=golden_encoder_eval, model=golden_model, decode=golden_decode, mbr=golden_mbr, bmuf=golden_bmuf)
+                 encoder=golden_encoder_eval, model=golden_model, decode=golden_decode, mbr=golden_mbr, bmuf=golden_bmuf,
+                 model_full=golden_model_full, decode_big=golden_decode_big)
     for w in which:
         table[w]()

@@ -100,3 +100,48 @@ def test_bmuf_two_ranks_gloo():
         p.join(30)
     for r in res:
         assert all(r[1:]), r
+
+
+def worker_empty(rank, world, port, q):
+    """rank 1 receives an EMPTY loader item exactly at a sync index; it must still enter the block sync (reference loop
+    trainer/train_transducer_bmuf_otfaug.py:112-123 syncs on every `num_done % sync_period == 0`, data or not)"""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import types
+    from pika_b200.trainer.bmuf import BmufTrainer
+    from pika_b200.trainer.step import TrainStep
+    torch.manual_seed(5)
+    model = torch.nn.Linear(6, 4)
+    tr = BmufTrainer(0, rank, world, model, 0.9, 1.0, backend="gloo", ops=NumpyOps)
+    resets = []
+    opt = types.SimpleNamespace(reset=lambda lr: resets.append(lr))
+    args = types.SimpleNamespace(sync_period=2, initial_lr=1e-3, final_lr=1e-4, epoch=0, num_batches_per_epoch=10, num_epochs=2)
+    step = TrainStep(model, args, None, tr, opt)
+    for item in range(5):                              # sync indices: 2 and 4
+        empty = (rank == 1 and item in (2, 3))         # rank 1: empty at a sync index and at a plain index
+        if not empty:
+            with torch.no_grad():
+                model.weight.add_(0.01 * (rank + 1) * (item + 1))     # stands in for forward/backward/SGD
+            step.end_of_item()
+        else:
+            step.skip()
+    mine = tr.flat.data.clone()
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    q.put((rank, step.num_done == 5, len(resets) == 2, torch.equal(gathered[0], gathered[1]), torch.equal(tr.param, tr.flat.data)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_empty_batch_on_one_rank_still_syncs():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=worker_empty, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(30)
+    for r in res:
+        assert all(r[1:]), r

@@ -14,6 +14,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _record(name, obj):
+    """measured parity figures land in gpurun_out/parity_measured.jsonl so that the stated tolerances can be checked against them"""
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_measured.jsonl"), "a") as f:
+        f.write(json.dumps({"name": name, **obj}) + "\n")
+
+
 def rel(a, b):
     a = torch.as_tensor(a).float().cpu(); b = torch.as_tensor(b).float().cpu()
     return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
@@ -40,21 +49,26 @@ def test_train_forward_backward_matches_reference(golden_dir, precision, tol_act
         y = torch.from_numpy(d["y"]).long().cuda()
         enc = engine.encoder_forward(m.encoder, x)
         assert rel(enc, d["enc"]) < tol_act
+        meas = {"enc": rel(enc, d["enc"])}
         for k in ("encoder.bn_in.running_mean", "encoder.hidden_bn.8.running_var", "encoder.bn_final.running_mean"):
             v = dict(m.named_buffers())[k]
             assert abs(v.double().sum().item() - d["bn_" + k][0]) < max(1e-3 * abs(d["bn_" + k][0]), 3e-2 if precision == "bf16" else 2e-3)
         pred = engine.prednet_forward_act(m, y)
         assert rel(pred, d["pred"]) < tol_act
+        meas["pred"] = rel(pred, d["pred"])
         m2 = build(); m2.train()
         logits = m2.forward(x, y, None, softmax=False)
         assert logits.dtype == torch.float32 and tuple(logits.shape) == d["logits"].shape
         assert rel(logits, d["logits"]) < tol_act
+        meas["logits"] = rel(logits, d["logits"])
         lp = m2.forward(x, y, None, softmax=True)
         assert rel(lp, torch.log_softmax(torch.from_numpy(d["logits"]), -1)) < tol_act
         # fused training path: loss + every parameter gradient
         m3 = build(); m3.train()
         costs = engine.transducer_loss(m3, x, y, torch.from_numpy(d["tlens"]).cuda(), torch.from_numpy(d["ulens"]).cuda())
         np.testing.assert_allclose(costs.detach().cpu().numpy(), d["costs"], rtol=tol_loss)
+        meas["loss"] = float(np.abs(costs.detach().cpu().numpy() / d["costs"] - 1).max())
+        _record("model_small_%s" % precision, meas)
         costs.sum().backward()
         gtol = 5e-3 if precision == "fp32" else 0.15
         bad = []
@@ -66,6 +80,26 @@ def test_train_forward_backward_matches_reference(golden_dir, precision, tol_act
             if abs(nrm - ref[0]) > gtol * max(ref[0], 1e-6) + (1e-5 if precision == "fp32" else 1e-3):
                 bad.append((k, nrm, ref[0]))
         assert not bad, bad
+        # full gradient DIRECTION, not just the norm: <= 512 strided samples of every parameter gradient (make_golden.py:golden_model)
+        from fixture_utils import grad_fingerprint
+        worst = {}
+        for k, p in m3.named_parameters():
+            ref = d["gs_" + k]
+            got = grad_fingerprint(p.grad.cpu(), 512)
+            rn = np.linalg.norm(ref[3:])
+            if ref[2] < 1e-6:                          # analytically zero gradient (a bias in front of a BatchNorm)
+                assert np.abs(got[3:]).max() < (1e-5 if precision == "fp32" else 2e-3), k
+                continue
+            if rn < 1e-3 * ref[2]:                     # the strided sample happens to hold none of the gradient's mass
+                continue
+            err = np.linalg.norm(got[3:] - ref[3:]) / rn
+            cos = float(np.dot(got[3:], ref[3:]) / (np.linalg.norm(got[3:]) * rn + 1e-30))
+            worst[k] = (err, cos)
+        w_err = max(v[0] for v in worst.values()); w_cos = min(v[1] for v in worst.values())
+        _record("model_small_grad_samples_%s" % precision, dict(worst_rel_err=w_err, worst_cos=w_cos,
+                                                                 worst_key=max(worst, key=lambda k: worst[k][0])))
+        assert w_err < (1e-2 if precision == "fp32" else 0.2), sorted(worst.items(), key=lambda kv: -kv[1][0])[:5]
+        assert w_cos > (0.9999 if precision == "fp32" else 0.98)
         # unfused compatibility path (model.forward + RNNTLoss.apply) gives the same loss
         from pika_b200.warp_rnnt import RNNTLoss
         m4 = build(); m4.train()
@@ -95,3 +129,59 @@ def test_encoder_eval_config1(golden_dir, precision, tol):
         assert rel(enc, d["enc"]) < tol
     finally:
         engine.set_precision("bf16")
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_full_shape_T1000_U150_V6000_matches_reference(golden_dir, precision):
+    """BASELINE shape (T=1000 frames -> T'=240, U=150, V=6000), B=2 with ragged lengths, against the reference's own modules
+    run on the CPU (tests/golden/model_full_shape.npz, make_golden.py:golden_model_full).  Exercises what the small fixtures
+    cannot: the 24-tile row-LSE epilogue of the fc2 GEMM inside the model, the 151-wide lattice, 6000-column gradients."""
+    from pika_b200 import engine
+    from fixture_utils import grad_fingerprint
+    from make_inputs import full_shape_inputs
+    d = np.load(os.path.join(golden_dir, "model_full_shape.npz"))
+    V = int(d["V"])
+    x_np, y_np, lens_np, ulens_np = full_shape_inputs(seed=int(d["seed"]), V=V)
+    engine.set_precision(precision)
+    engine.set_dropout_enabled(False)
+    try:
+        m = build(V)
+        m.train()
+        x, y = torch.from_numpy(x_np).cuda(), torch.from_numpy(y_np).cuda()
+        tl, ul = torch.from_numpy(d["tlens"]).cuda(), torch.from_numpy(ulens_np).cuda()
+        enc = engine.encoder_forward_act(m.encoder, x)
+        pred = engine.prednet_forward_act(m, y)
+        logits = engine.JointFn.apply(enc, pred, m)[..., :V]
+        meas = dict(enc=rel(enc[:, ::5, ::7], d["enc"]), pred=rel(pred[:, ::3, ::7], d["pred"]),
+                    logits=rel(logits[:, ::9, ::7, ::53], d["logits"]),
+                    lse=rel(torch.logsumexp(logits[:, ::9, ::7].float(), -1), d["lse"]))
+        del logits, enc, pred
+        m3 = build(V); m3.train()
+        costs = engine.transducer_loss(m3, x, y, tl, ul)
+        got = costs.detach().cpu().numpy()
+        meas["loss"] = float(np.abs(got / d["costs"] - 1).max())
+        costs.sum().backward()
+        worst = {}
+        for k, p in m3.named_parameters():
+            ref = d["gs_" + k]
+            g = grad_fingerprint(p.grad.cpu(), 256)
+            rn = np.linalg.norm(ref[3:])
+            if ref[2] < 1e-6 or rn < 1e-3 * ref[2]:
+                continue
+            worst[k] = float(np.linalg.norm(g[3:] - ref[3:]) / rn)
+        meas["grad_worst"] = max(worst.values())
+        meas["grad_worst_key"] = max(worst, key=worst.get)
+        meas["grad_fc2_bias"] = worst.get("fc2.bias")
+        # the fc2 bias gradient IS the column sum of dlogits over all 72 480 rows: a 6000-wide signature of the fused loss gradient
+        cs = m3.fc2.bias.grad.double().cpu().numpy()
+        meas["dlogits_colsum"] = float(np.linalg.norm(cs - d["dlogits_colsum"]) / np.linalg.norm(d["dlogits_colsum"]))
+        _record("model_full_shape_%s" % precision, meas)
+        act_tol, loss_tol, grad_tol = (1e-3, 1e-3, 2e-2) if precision == "fp32" else (6e-2, 2e-3, 0.2)
+        assert meas["enc"] < act_tol and meas["pred"] < act_tol and meas["logits"] < act_tol, meas
+        assert meas["lse"] < (1e-4 if precision == "fp32" else 2e-3), meas
+        assert meas["loss"] < loss_tol, meas
+        assert meas["dlogits_colsum"] < (2e-3 if precision == "fp32" else 3e-2), meas
+        assert meas["grad_worst"] < grad_tol, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    finally:
+        engine.set_precision("bf16")
+        engine.set_dropout_enabled(True)
