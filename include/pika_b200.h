@@ -88,13 +88,16 @@ typedef struct {
     int block_n;                      /* 0 = auto; else 64 | 128 | 256 */
     int k_splits;                     /* 0 = auto; 1 = off; >1 = split the reduction (plain f32 2-D C only) */
     int two_sm;                       /* 0 = auto (CTA-pair kernel for 256-wide tiles when M > 128); 1 = force; -1 = never */
-    float* row_lse;                   /* optional out [ceil(N/block_n)][M][2] f32: per row and N-tile (max*log2(e), sum_j 2^(c_ij*log2(e) - max))
-                                         over the ROUNDED bf16 outputs -- the first pass of the fused log-softmax + RNN-T loss
-                                         (pk_rnnt_loss_fwd_bwd_lse) computed while the logits tile is still in TMEM.
-                                         Needs a 2-D bf16 C with N % 8 == 0; block_n is 256 unless forced. */
+    float* row_lse;                   /* optional out [pk_gemm_row_lse_parts()][M][2] f32: per row and column group (max*log2(e),
+                                         sum_j 2^(c_ij*log2(e) - max)) over the ROUNDED bf16 outputs -- the first pass of the fused
+                                         log-softmax + RNN-T loss (pk_rnnt_loss_fwd_bwd_lse) computed while the logits tile is still in TMEM.
+                                         Needs a 2-D bf16 C with N % 8 == 0, K-major operands, block_n 256. */
 } pk_gemm_desc;
 
 int pk_gemm_bf16(const pk_gemm_desc* desc, void* stream);
+/* number of partials per row that pk_gemm_bf16 writes into row_lse for an [M, N] output with these block_n / two_sm settings:
+ * one per 256-wide N tile on the single-CTA kernel, two on the CTA-pair kernel (two epilogue groups per tile) */
+int pk_gemm_row_lse_parts(long long M, long long N, int block_n, int two_sm);
 
 /* ------------------------------------------------------------------------------------------
  * RNN-T loss + gradient, fused with the log-softmax over V.

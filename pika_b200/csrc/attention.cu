@@ -41,6 +41,7 @@ struct AttnParams {
     float* lse;                                      // [B*heads*T] natural-log row log-sum-exp of the scaled scores
     float* dsum;                                     // [B*heads*T] D_i
     int B, T, heads;
+    int stat_ld;                                     // row pitch of lse / dsum per (batch, head): pk_attention_lse_stride(T)
     float alpha;
     uint32_t drop_thresh; float drop_scale; uint32_t seed;
 };
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_kernel(const AttnPara
     const __nv_bfloat16* gk = p.k + head_off;
     const __nv_bfloat16* gv = p.v + head_off;
     const __nv_bfloat16* gdo = (MODE == 0) ? nullptr : p.dout + (long long)b * T * p.ld_do + h * 64;
-    const long long stat_row0 = (long long)bh * T;             // row offset into lse / dsum / the dropout index space
+    const long long stat_row0 = (long long)bh * T;             // row offset into the dropout index space
+    const long long stat_vec0 = (long long)bh * p.stat_ld;     // row offset into lse / dsum
     const uint32_t sbase = smem_u32(smem);
 
     // ---- stationary fragments: A1 (Q | Q | K), A2 (- | dO | V)
@@ -192,8 +194,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_kernel(const AttnPara
     float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;           // MODE 0 online softmax state
     float lse_lo = 0.f, lse_hi = 0.f, d_lo = 0.f, d_hi = 0.f;                   // MODE 1 row scalars (log2 domain lse)
     if (MODE == 1) {
-        if (my_row_lo < T) { lse_lo = p.lse[stat_row0 + my_row_lo] * AT_LOG2E; d_lo = p.dsum[stat_row0 + my_row_lo]; }
-        if (my_row_hi < T) { lse_hi = p.lse[stat_row0 + my_row_hi] * AT_LOG2E; d_hi = p.dsum[stat_row0 + my_row_hi]; }
+        if (my_row_lo < T) { lse_lo = p.lse[stat_vec0 + my_row_lo] * AT_LOG2E; d_lo = p.dsum[stat_vec0 + my_row_lo]; }
+        if (my_row_hi < T) { lse_hi = p.lse[stat_vec0 + my_row_hi] * AT_LOG2E; d_hi = p.dsum[stat_vec0 + my_row_hi]; }
     }
 
     const __nv_bfloat16* gx1 = (MODE == 2) ? gq : gk;          // streamed operand of the score product
@@ -207,8 +209,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_kernel(const AttnPara
         load_tile<AT_TILE>(st + AT_TILE * 128, gx2, ld_x2, j * AT_TILE, T);
         if (MODE == 2 && threadIdx.x < AT_TILE) {
             const int r = j * AT_TILE + threadIdx.x;
-            s_lse[j & 1][threadIdx.x] = r < T ? p.lse[stat_row0 + r] * AT_LOG2E : 0.f;
-            s_dsum[j & 1][threadIdx.x] = r < T ? p.dsum[stat_row0 + r] : 0.f;
+            s_lse[j & 1][threadIdx.x] = r < T ? p.lse[stat_vec0 + r] * AT_LOG2E : 0.f;
+            s_dsum[j & 1][threadIdx.x] = r < T ? p.dsum[stat_vec0 + r] : 0.f;
         }
         cp_async_commit();
     };
@@ -309,8 +311,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_kernel(const AttnPara
         l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
         store_rows(p.out + (long long)b * T * p.ld_o + h * 64, p.ld_o, wrow0, T, lane, acc1, p.drop_scale / l_lo, p.drop_scale / l_hi);
         if (t == 0) {
-            if (my_row_lo < T) p.lse[stat_row0 + my_row_lo] = (m_lo + log2f(l_lo)) * AT_LN2;
-            if (my_row_hi < T) p.lse[stat_row0 + my_row_hi] = (m_hi + log2f(l_hi)) * AT_LN2;
+            if (my_row_lo < T) p.lse[stat_vec0 + my_row_lo] = (m_lo + log2f(l_lo)) * AT_LN2;
+            if (my_row_hi < T) p.lse[stat_vec0 + my_row_hi] = (m_hi + log2f(l_hi)) * AT_LN2;
         }
     } else if (MODE == 1) {
         store_rows(p.dq + (long long)b * T * p.ld_dqkv + h * 64, p.ld_dqkv, wrow0, T, lane, acc1, p.alpha, p.alpha);
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_kernel(const AttnPara
 // D[(b*heads + h)*T + t] = sum_d dO[b,t,h,d] * O[b,t,h,d]; one warp per (b, t, h)
 __global__ void __launch_bounds__(256) attention_rowdot_kernel(const __nv_bfloat16* __restrict__ o, long long ld_o,
                                                                const __nv_bfloat16* __restrict__ dout, long long ld_do, float* __restrict__ dsum,
-                                                               int B, int T, int heads) {
+                                                               int B, int T, int heads, int stat_ld) {
     const int lane = threadIdx.x & 31;
     const long long n = (long long)B * T * heads;
     for (long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); w < n; w += (long long)gridDim.x * 8) {
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(256) attention_rowdot_kernel(const __nv_bfloat
         const uint32_t ov = *reinterpret_cast<const uint32_t*>(o + bt * ld_o + h * 64 + lane * 2);
         const uint32_t dv = *reinterpret_cast<const uint32_t*>(dout + bt * ld_do + h * 64 + lane * 2);
         const float s = warp_sum(bf16lo(ov) * bf16lo(dv) + bf16hi(ov) * bf16hi(dv));
-        if (lane == 0) dsum[((long long)b * heads + h) * T + tt] = s;
+        if (lane == 0) dsum[((long long)b * heads + h) * stat_ld + tt] = s;
     }
 }
 
@@ -357,14 +359,14 @@ static uint32_t attn_drop_thresh(float p) {
     PK_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "drop_p out of range");                                                    \
     PK_CHECK_ARG((long long)B * heads < 65536, "B * heads must be < 65536")
 
-extern "C" int pk_attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, float* lse,
+extern "C" int pk_attention_hmma_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, float* lse,
                                 int B, int T, int heads, int dh, float alpha, float drop_p, uint32_t seed, void* stream) {
     using namespace pk;
     ATTN_CHECKS();
     AttnParams p{};
     p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.ld_qkv = ld_qkv;
     p.out = (__nv_bfloat16*)out; p.ld_o = ld_out; p.lse = lse;
-    p.B = B; p.T = T; p.heads = heads; p.alpha = alpha;
+    p.B = B; p.T = T; p.heads = heads; p.alpha = alpha; p.stat_ld = (T + 63) / 64 * 64;
     p.drop_thresh = attn_drop_thresh(drop_p); p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f; p.seed = seed;
     dim3 grid((T + AT_ROWS - 1) / AT_ROWS, B * heads);
     attention_kernel<0><<<grid, AT_THREADS, 0, STREAM(stream)>>>(p);
@@ -372,7 +374,7 @@ extern "C" int pk_attention_fwd(const void* q, const void* k, const void* v, lon
 }
 
 /* dq/dk/dv share the row stride ld_dqkv (the fused [B,T,3D] gradient buffer); dsum_ws: B*heads*T floats of scratch */
-extern "C" int pk_attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
+extern "C" int pk_attention_hmma_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
                                 const void* dout, long long ld_dout, const float* lse, float* dsum_ws, void* dq, void* dk, void* dv,
                                 long long ld_dqkv, int B, int T, int heads, int dh, float alpha, float drop_p, uint32_t seed, void* stream) {
     using namespace pk;
@@ -383,11 +385,11 @@ extern "C" int pk_attention_bwd(const void* q, const void* k, const void* v, lon
     p.o = (const __nv_bfloat16*)out; p.ld_o = ld_out; p.dout = (const __nv_bfloat16*)dout; p.ld_do = ld_dout;
     p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.ld_dqkv = ld_dqkv;
     p.lse = const_cast<float*>(lse); p.dsum = dsum_ws;
-    p.B = B; p.T = T; p.heads = heads; p.alpha = alpha;
+    p.B = B; p.T = T; p.heads = heads; p.alpha = alpha; p.stat_ld = (T + 63) / 64 * 64;
     p.drop_thresh = attn_drop_thresh(drop_p); p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f; p.seed = seed;
     const long long n = (long long)B * T * heads;
     const int rgrid = (int)((n + 7) / 8 < 148ll * 16 ? (n + 7) / 8 : 148ll * 16);
-    attention_rowdot_kernel<<<rgrid, 256, 0, STREAM(stream)>>>(p.o, ld_out, p.dout, ld_dout, dsum_ws, B, T, heads);
+    attention_rowdot_kernel<<<rgrid, 256, 0, STREAM(stream)>>>(p.o, ld_out, p.dout, ld_dout, dsum_ws, B, T, heads, p.stat_ld);
     PK_CHECK_LAUNCH(); count_launch();
     dim3 grid((T + AT_ROWS - 1) / AT_ROWS, B * heads);
     attention_kernel<1><<<grid, AT_THREADS, 0, STREAM(stream)>>>(p);

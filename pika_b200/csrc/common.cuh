@@ -30,6 +30,8 @@ void set_last_error(const char* fmt, ...);
 #define PK_CHECK_LAUNCH() PK_CHECK_CUDA(cudaGetLastError())
 
 int num_sms();
+int encode_tiled_bf16_3d(CUtensorMap* out, const void* ptr, const unsigned long long (&dims)[3], const unsigned long long (&strides_bytes)[2],
+                         const unsigned (&box)[3], const char* what);
 
 // ---------------------------------------------------------------- dtype helpers
 enum DType : int { F32 = 0, BF16 = 1 };
@@ -65,6 +67,22 @@ PK_DEVICE uint32_t hash_u32(uint64_t idx, uint32_t seed) {
 }
 // keep iff hash >= thresh where thresh = p * 2^32
 PK_DEVICE bool drop_keep(uint64_t idx, uint32_t seed, uint32_t thresh) { return hash_u32(idx, seed) >= thresh; }
+
+// Attention-probability dropout: one hash per PAIR of adjacent keys of a probability row, 16 bits per element (halves the
+// integer work of the mask, which is the largest ALU item of the fused attention kernels).  `grow` = row of the
+// [B*heads*T, T] probability matrix, kp = key >> 1, Tp2 = ceil(T / 2); returns keep bits (bit 0: even key, bit 1: odd key).
+// keep iff the 16-bit lane >= thresh16 = round(p * 65536); the keep-scale is 1 / (1 - thresh16 / 65536).
+PK_DEVICE uint32_t drop_pair(uint64_t grow, uint32_t Tp2, uint32_t kp, uint32_t seed, uint32_t thresh16) {
+    const uint32_t h = hash_u32(grow * (uint64_t)Tp2 + kp, seed);
+    return ((h & 0xFFFFu) >= thresh16 ? 1u : 0u) | ((h >> 16) >= thresh16 ? 2u : 0u);
+}
+__host__ __device__ inline uint32_t drop_thresh16_of(float p) {
+    if (p <= 0.f) return 0u;
+    const double t = (double)p * 65536.0 + 0.5;
+    const uint32_t r = t >= 65535.0 ? 65535u : (uint32_t)t;
+    return r == 0 ? 1u : r;
+}
+__host__ __device__ inline float drop_scale16_of(uint32_t thresh16) { return thresh16 ? 1.f / (1.f - (float)thresh16 / 65536.f) : 1.f; }
 
 PK_DEVICE float warp_sum(float v) {
 #pragma unroll
@@ -129,6 +147,19 @@ PK_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+PK_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// plain (non-tensor) bulk copy global -> shared, bytes % 16 == 0, both addresses 16-byte aligned
+PK_DEVICE void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 PK_DEVICE void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -141,6 +172,24 @@ PK_DEVICE void tma_reduce_add_4d(const CUtensorMap* m, const void* smem_src, int
         "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
             reinterpret_cast<uint64_t>(m)),
         "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// L2 eviction-priority policies (the encodings createpolicy.fractional.L2::evict_{normal,first,last} produce for fraction 1.0)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+PK_DEVICE void tma_load_4d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+        : "memory");
+}
+PK_DEVICE void tma_store_4d_hint(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::"l"(
+            reinterpret_cast<uint64_t>(m)),
+        "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
         : "memory");
 }
 PK_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -241,6 +290,13 @@ PK_DEVICE void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* b
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+PK_DEVICE void tma_load_4d_2sm_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
         : "memory");
 }
 // arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster

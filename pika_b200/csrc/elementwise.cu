@@ -163,53 +163,111 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ run_mean, const f
     rstd[c] = rsqrtf(run_var[c] + eps);
 }
 
-// y = (x - mean) * rstd * w + b
+// Column-resident streaming kernels: a thread owns 8 consecutive channels (its per-channel coefficients live in registers) and
+// walks a slice of the rows with UR 16-byte loads in flight -- no per-element coefficient loads, no index arithmetic in the loop.
+// Block = 128 threads = 1024 channels (gridDim.x covers C), gridDim.y slices the rows.
+//
+// y = (x - mean) * rstd * w + b  ==  x * sc + sh
 template <typename T>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int C,
+__global__ void __launch_bounds__(128) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int C,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                                        const float* __restrict__ w, const float* __restrict__ b) {
-    const long long nvec = rows * C / 8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)((i * 8) % C);
-        float f[8];
-        V8<T>::load(x + i * 8, f);
+    const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+    if (c0 >= C) return;
+    float sc[8], sh[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float sc = rstd[c0 + e] * w[c0 + e];
-            f[e] = (f[e] - mean[c0 + e]) * sc + b[c0 + e];
+    for (int e = 0; e < 8; ++e) {
+        sc[e] = rstd[c0 + e] * w[c0 + e];
+        sh[e] = b[c0 + e] - mean[c0 + e] * sc[e];
+    }
+    const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
+    const long long r0 = (long long)blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+    constexpr int UR = 8;
+    long long r = r0;
+    for (; r + UR <= r1; r += UR) {
+        float f[UR][8];
+#pragma unroll
+        for (int k = 0; k < UR; ++k) V8<T>::load(x + (r + k) * C + c0, f[k]);
+#pragma unroll
+        for (int k = 0; k < UR; ++k) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[k][e] = fmaf(f[k][e], sc[e], sh[e]);
+            V8<T>::store(y + (r + k) * C + c0, f[k]);
         }
-        V8<T>::store(y + i * 8, f);
+    }
+    for (; r < r1; ++r) {
+        float f[8];
+        V8<T>::load(x + r * C + c0, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+        V8<T>::store(y + r * C + c0, f);
     }
 }
 
-// BN backward (train): dx = w*rstd*(dy - sdy/n - xhat*sdyx/n); optionally masked by relu_mask (x > 0,
-// x being the BN input = ReLU output, so this also back-propagates through the ReLU).
+// BN backward (train): dx = w*rstd*(dy - sdy/n - xhat*sdyx/n) == A*dy + Bx*x + C0 per channel; optionally masked by
+// relu_mask (x > 0, x being the BN input = ReLU output, so this also back-propagates through the ReLU).
 // eval mode (sdy == nullptr): dx = w*rstd*dy.
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+__global__ void __launch_bounds__(128) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
                                                            long long rows, int C, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ w,
                                                            const float* __restrict__ sdy, const float* __restrict__ sdyx,
                                                            int relu_mask) {
-    const long long nvec = rows * C / 8;
+    const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+    if (c0 >= C) return;
     const float inv_n = 1.f / (float)rows;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)((i * 8) % C);
+    float ca[8], cb[8], cc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        const float a = w[c] * rstd[c];
+        ca[e] = a;
+        if (sdy) {
+            const float k = rstd[c] * sdyx[c] * inv_n;         // coefficient of xhat's (x - mean)
+            cb[e] = -a * k;
+            cc[e] = a * (mean[c] * k - sdy[c] * inv_n);
+        } else {
+            cb[e] = 0.f; cc[e] = 0.f;
+        }
+    }
+    const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
+    const long long r0 = (long long)blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+    constexpr int UR = 4;
+    long long r = r0;
+    for (; r + UR <= r1; r += UR) {
+        float g[UR][8], f[UR][8];
+#pragma unroll
+        for (int k = 0; k < UR; ++k) { V8<T>::load(dy + (r + k) * C + c0, g[k]); V8<T>::load(x + (r + k) * C + c0, f[k]); }
+#pragma unroll
+        for (int k = 0; k < UR; ++k) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = fmaf(g[k][e], ca[e], fmaf(f[k][e], cb[e], cc[e]));
+                g[k][e] = (relu_mask && !(f[k][e] > 0.f)) ? 0.f : d;
+            }
+            V8<T>::store(dx + (r + k) * C + c0, g[k]);
+        }
+    }
+    for (; r < r1; ++r) {
         float g[8], f[8];
-        V8<T>::load(dy + i * 8, g);
-        V8<T>::load(x + i * 8, f);
+        V8<T>::load(dy + r * C + c0, g);
+        V8<T>::load(x + r * C + c0, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int c = c0 + e;
-            const float xh = (f[e] - mean[c]) * rstd[c];
-            float d = g[e];
-            if (sdy) d = d - sdy[c] * inv_n - xh * sdyx[c] * inv_n;
-            d *= w[c] * rstd[c];
-            if (relu_mask && !(f[e] > 0.f)) d = 0.f;
-            g[e] = d;
+            const float d = fmaf(g[e], ca[e], fmaf(f[e], cb[e], cc[e]));
+            g[e] = (relu_mask && !(f[e] > 0.f)) ? 0.f : d;
         }
-        V8<T>::store(dx + i * 8, g);
+        V8<T>::store(dx + r * C + c0, g);
     }
+}
+// (column blocks, row slices) for the two kernels above: enough CTAs for ~8 per SM
+static inline dim3 col_grid(long long rows, int C) {
+    const int gx = (C + 1023) / 1024;
+    long long gy = ((long long)num_sms() * 8 + gx - 1) / gx;
+    const long long max_gy = (rows + 15) / 16;                 // at least 16 rows per slice
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    return dim3(gx, (unsigned)gy);
 }
 
 // =============================================================================== LayerNorm (C <= 8192, C % 8 == 0)
@@ -365,7 +423,14 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
                 for (int e = 0; e < 8; ++e) {
                     o[e] = to_f32<T>(from_f32<T>(v[k][e] * inv));        // dropout acts on the rounded probability
                     od[e] = o[e];
-                    if (drop_thresh) od[e] = drop_keep((uint64_t)r * (uint64_t)n + c0 + e, seed, drop_thresh) ? o[e] * drop_scale : 0.f;
+                }
+                if (drop_thresh) {                                       // pair mask shared with the fused attention kernels (common.cuh)
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        const uint32_t km = drop_pair((uint64_t)r, (uint32_t)((n + 1) >> 1), (uint32_t)((c0 >> 1) + e2), seed, drop_thresh);
+                        od[2 * e2] = (km & 1u) ? o[2 * e2] * drop_scale : 0.f;
+                        od[2 * e2 + 1] = (km & 2u) ? o[2 * e2 + 1] * drop_scale : 0.f;
+                    }
                 }
                 V8<T>::store(P + r * ld_p + c0, o);
                 if (Pd != P) V8<T>::store(Pd + r * ld_p + c0, od);
@@ -391,9 +456,17 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
                 ld8f(dPd + r * ld_d + c0, d[k]);
                 V8<T>::load(P + r * ld_p + c0, pv[k]);
 #pragma unroll
+                if (drop_thresh) {
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        const uint32_t km = drop_pair((uint64_t)r, (uint32_t)((n + 1) >> 1), (uint32_t)((c0 >> 1) + e2), seed, drop_thresh);
+                        d[k][2 * e2] = (km & 1u) ? d[k][2 * e2] * drop_scale : 0.f;
+                        d[k][2 * e2 + 1] = (km & 2u) ? d[k][2 * e2 + 1] * drop_scale : 0.f;
+                    }
+                }
+#pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     if (c0 + e >= n) { d[k][e] = 0.f; pv[k][e] = 0.f; }
-                    else if (drop_thresh) d[k][e] = drop_keep((uint64_t)r * (uint64_t)n + c0 + e, seed, drop_thresh) ? d[k][e] * drop_scale : 0.f;
                     dot += d[k][e] * pv[k][e];
                 }
             }
@@ -413,24 +486,57 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
 }
 
 // =============================================================================== misc elementwise
-// y = dropout(x) with the GEMM epilogue's index convention (flat index of a contiguous tensor)
+// y = dropout(x) with the GEMM epilogue's index convention (flat index of a contiguous tensor); 8 elements per thread
+// (scalar tail for n % 8), 16-byte accesses.
 template <typename T>
-__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, uint32_t thresh, float scale, uint32_t seed) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, uint32_t thresh, float scale, uint32_t seed) {
+    const long long nv = n / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        float f[8];
+        V8<T>::load(x + i * 8, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = drop_keep((uint64_t)(i * 8 + e), seed, thresh) ? f[e] * scale : 0.f;
+        V8<T>::store(y + i * 8, f);
+    }
+    for (long long i = nv * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float v = to_f32<T>(x[i]);
         y[i] = from_f32<T>(drop_keep((uint64_t)i, seed, thresh) ? v * scale : 0.f);
     }
 }
 // dx = dy * (y != 0) * scale     (backward of ReLU and of ReLU+dropout given the saved output y)
 template <typename T>
-__global__ void mask_nz_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n, float scale) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+__global__ void __launch_bounds__(256) mask_nz_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n, float scale) {
+    const long long nv = n / 8;
+    constexpr int UR = 2;
+    for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * UR; i0 < nv; i0 += (long long)gridDim.x * blockDim.x * UR) {
+        float g[UR][8], f[UR][8];
+#pragma unroll
+        for (int k = 0; k < UR; ++k)
+            if (i0 + k < nv) { V8<T>::load(dy + (i0 + k) * 8, g[k]); V8<T>::load(y + (i0 + k) * 8, f[k]); }
+#pragma unroll
+        for (int k = 0; k < UR; ++k)
+            if (i0 + k < nv) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[k][e] = f[k][e] != 0.f ? g[k][e] * scale : 0.f;
+                V8<T>::store(dx + (i0 + k) * 8, g[k]);
+            }
+    }
+    for (long long i = nv * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dx[i] = from_f32<T>(to_f32<T>(y[i]) != 0.f ? to_f32<T>(dy[i]) * scale : 0.f);
 }
 // out = a + b
 template <typename T>
-__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+__global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
+    const long long nv = n / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        float f[8], g[8];
+        V8<T>::load(a + i * 8, f);
+        V8<T>::load(b + i * 8, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += g[e];
+        V8<T>::store(o + i * 8, f);
+    }
+    for (long long i = nv * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         o[i] = from_f32<T>(to_f32<T>(a[i]) + to_f32<T>(b[i]));
 }
 // log_softmax rows: x T [rows, ld] (first n valid) -> y f32 [rows, n] * 1
@@ -756,8 +862,7 @@ extern "C" int pk_bn_fwd(const void* x, void* y, int dtype, long long rows, int 
         bn_eval_stats_kernel<<<(C + 255) / 256, 256, 0, st>>>(run_mean, run_var, C, eps, mean, rstd);
     }
     PK_CHECK_LAUNCH(); count_launch();
-    const int grid = grid_for(rows * C / 8, 256);
-    PK_DISPATCH_T(dtype, (bn_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (T*)y, rows, C, mean, rstd, w, b)));
+    PK_DISPATCH_T(dtype, (bn_apply_kernel<T><<<col_grid(rows, C), 128, 0, st>>>((const T*)x, (T*)y, rows, C, mean, rstd, w, b)));
     DONE();
 }
 
@@ -768,8 +873,7 @@ extern "C" int pk_bn_bwd(const void* dy, const void* x, void* dx, int dtype, lon
     PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
     cudaStream_t st = STREAM(stream);
     PK_DISPATCH_T(dtype, { int rc = run_colstats<T, 1>((const T*)dy, (const T*)x, rows, C, mean, rstd, ws, db, dw, st); if (rc) return rc; });
-    const int grid = grid_for(rows * C / 8, 256);
-    PK_DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, (T*)dx, rows, C, mean, rstd, w,
+    PK_DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<col_grid(rows, C), 128, 0, st>>>((const T*)dy, (const T*)x, (T*)dx, rows, C, mean, rstd, w,
                                                                        train ? db : nullptr, train ? dw : nullptr, relu_mask)));
     DONE();
 }
@@ -804,8 +908,8 @@ extern "C" int pk_softmax_fwd(const float* S, long long ld_s, void* P, void* Pd,
                               float drop_p, uint32_t seed, void* stream) {
     PK_CHECK_ARG(rows > 0 && n > 0 && ld_p >= n && ld_s >= ld_p && ld_p <= 2048 && ld_p % 8 == 0 && ld_s % 8 == 0, "softmax rows: ld % 8 == 0, <= 2048 wide");
     const int grid = grid_for(rows, 8);
-    const uint32_t th = drop_thresh_of(drop_p);
-    const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t th = drop_thresh16_of(drop_p);     // 16-bit pair mask (common.cuh drop_pair)
+    const float sc = drop_scale16_of(th);
     if (ld_p <= 1024) { PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T, 4><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed))); }
     else { PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T, 8><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed))); }
     DONE();
@@ -813,8 +917,8 @@ extern "C" int pk_softmax_fwd(const float* S, long long ld_s, void* P, void* Pd,
 extern "C" int pk_softmax_bwd(const float* dPd, long long ld_d, const void* P, long long ld_p, void* dS, int dtype, long long rows,
                               int n, float drop_p, uint32_t seed, void* stream) {
     const int grid = grid_for(rows, 8);
-    const uint32_t th = drop_thresh_of(drop_p);
-    const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t th = drop_thresh16_of(drop_p);     // 16-bit pair mask (common.cuh drop_pair)
+    const float sc = drop_scale16_of(th);
     PK_CHECK_ARG(ld_p <= 2048 && ld_p % 8 == 0 && ld_d % 8 == 0, "softmax rows: ld % 8 == 0, <= 2048 wide");
     if (ld_p <= 1024) { PK_DISPATCH_T(dtype, (softmax_bwd_kernel<T, 4><<<grid, 256, 0, STREAM(stream)>>>(dPd, ld_d, (const T*)P, ld_p, (T*)dS, rows, n, th, sc, seed))); }
     else { PK_DISPATCH_T(dtype, (softmax_bwd_kernel<T, 8><<<grid, 256, 0, STREAM(stream)>>>(dPd, ld_d, (const T*)P, ld_p, (T*)dS, rows, n, th, sc, seed))); }
@@ -822,19 +926,22 @@ extern "C" int pk_softmax_bwd(const float* dPd, long long ld_d, const void* P, l
 }
 
 extern "C" int pk_dropout(const void* x, void* y, int dtype, long long n, float p, uint32_t seed, void* stream) {
-    const int grid = grid_for(n, 1024);
+    const int grid = grid_for(n, 256 * 8);
     const uint32_t th = drop_thresh_of(p);
     PK_CHECK_ARG(th != 0, "p must be > 0");
+    PK_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "pk_dropout: pointers must be 16-byte aligned");
     PK_DISPATCH_T(dtype, (dropout_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)x, (T*)y, n, th, 1.f / (1.f - p), seed)));
     DONE();
 }
 extern "C" int pk_mask_nz(const void* dy, const void* y, void* dx, int dtype, long long n, float scale, void* stream) {
-    const int grid = grid_for(n, 1024);
+    const int grid = grid_for(n, 256 * 16);
+    PK_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0, "pk_mask_nz: pointers must be 16-byte aligned");
     PK_DISPATCH_T(dtype, (mask_nz_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)dy, (const T*)y, (T*)dx, n, scale)));
     DONE();
 }
 extern "C" int pk_add(const void* a, const void* b, void* o, int dtype, long long n, void* stream) {
-    const int grid = grid_for(n, 1024);
+    const int grid = grid_for(n, 256 * 8);
+    PK_CHECK_ARG(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(o)) & 15) == 0, "pk_add: pointers must be 16-byte aligned");
     PK_DISPATCH_T(dtype, (add_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)a, (const T*)b, (T*)o, n)));
     DONE();
 }

@@ -342,10 +342,10 @@ __global__ void __launch_bounds__(2 * LAT_MAX_G) rnnt_lattice_kernel(
 
 // ------------------------------------------------------------------------------------ pass 3
 // One CTA walks a contiguous block of joint nodes; thread i owns the 16-byte column groups i, i+256, ... of every
-// row (GRAD_MAXG groups -> V <= 256*8*GRAD_MAXG for bf16), so the column sums of dlogits (= the fc2 bias
+// row (32 columns per thread -> V <= 8192), so the column sums of dlogits (= the fc2 bias
 // gradient) accumulate in registers for free.  GRAD_RU rows are in flight per thread.
 constexpr int GRAD_THREADS = 256;
-constexpr int GRAD_MAXG = 4;
+template <typename T> struct GradCfg { static constexpr int MAXG = 32 / Vec16<T>::N; };   // 16-byte groups per thread: V <= 8192 for bf16 and f32
 template <typename T, int GRAD_RU, int MINB>
 __global__ void __launch_bounds__(GRAD_THREADS, MINB) rnnt_grad_kernel(const T* logits, const int* __restrict__ labels,
                                                                     const int* __restrict__ label_lens, RnntDims d,
@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, MINB) rnnt_grad_kernel(const T* 
                                                                     const float* __restrict__ gl_in, T* dlogits, float* __restrict__ colsum,
                                                                     long long rows_per_cta) {
     constexpr int VN = Vec16<T>::N;
+    constexpr int GRAD_MAXG = GradCfg<T>::MAXG;
     extern __shared__ float gsm[];                          // per-row scalars of this CTA's block: gb, gl, lse*log2e, label
     float* s_gb = gsm;
     float* s_gl = gsm + rows_per_cta;
@@ -454,18 +455,33 @@ __global__ void __launch_bounds__(GRAD_THREADS, MINB) rnnt_grad_kernel(const T* 
     }
 }
 
-// out[c] = sum over the n_part partial rows, in index order (4 independent chains per thread for latency, fixed association)
+// out[c] = sum over the n_part partial rows.  Block = 32 columns x 8 row groups; every group adds its rows in index order and the
+// eight group sums are combined in a fixed order, so the result is bit-reproducible.
 __global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ part, int n_part, int ld, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ld) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int i = 0;
-    for (; i + 4 <= n_part; i += 4) {
-        a0 += part[(size_t)(i + 0) * ld + c]; a1 += part[(size_t)(i + 1) * ld + c];
-        a2 += part[(size_t)(i + 2) * ld + c]; a3 += part[(size_t)(i + 3) * ld + c];
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float a = 0.f;
+    if (c < ld) {
+        const int per = (n_part + 7) / 8;
+        const int i0 = ty * per, i1 = min(n_part, i0 + per);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int i = i0;
+        for (; i + 4 <= i1; i += 4) {
+            a0 += part[(size_t)(i + 0) * ld + c]; a1 += part[(size_t)(i + 1) * ld + c];
+            a2 += part[(size_t)(i + 2) * ld + c]; a3 += part[(size_t)(i + 3) * ld + c];
+        }
+        for (; i < i1; ++i) a0 += part[(size_t)i * ld + c];
+        a = (a0 + a1) + (a2 + a3);
     }
-    for (; i < n_part; ++i) a0 += part[(size_t)i * ld + c];
-    out[c] = (a0 + a1) + (a2 + a3);
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < ld) {
+        float t = sm[0][tx];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += sm[k][tx];
+        out[c] = t;
+    }
 }
 
 }  // namespace pk
@@ -545,7 +561,7 @@ static int rnnt_loss_impl(const void* logits, int dtype, const int* labels, cons
                                                      costs, gb, gl);
     PK_CHECK_LAUNCH(); count_launch();
     if (dlogits != nullptr) {
-        PK_CHECK_ARG(ldv / vn <= GRAD_THREADS * GRAD_MAXG, "V too large for the gradient kernel (V <= 8192 bf16 / 4096 f32)");
+        PK_CHECK_ARG(ldv <= 8192, "V too large for the gradient kernel (V <= 8192)");
         int ru, ctas_per_sm, ggrid, variant; long long rpc;
         rnnt_grad_grid(rows, &ru, &ctas_per_sm, &rpc, &ggrid, &variant);
         (void)ru; (void)ctas_per_sm;
@@ -571,7 +587,7 @@ static int rnnt_loss_impl(const void* logits, int dtype, const int* labels, cons
 #undef PK_GRAD_LAUNCH
         PK_CHECK_LAUNCH(); count_launch();
         if (dlogits_colsum) {
-            colsum_partials_kernel<<<(ldv + 255) / 256, 256, 0, stream>>>(cs_part, ggrid, ldv, dlogits_colsum);
+            colsum_partials_kernel<<<(ldv + 31) / 32, 256, 0, stream>>>(cs_part, ggrid, ldv, dlogits_colsum);
             PK_CHECK_LAUNCH(); count_launch();
         }
     }

@@ -35,11 +35,16 @@ class TransducerDecoder():
             raise NotImplementedError("pika_b200: only the LSTM prediction net is supported")
 
     @torch.no_grad()
-    def decode_batch(self, x, x_len, max_len=None):
+    def decode_batch(self, x, x_len, max_len=None, enc_out=None):
+        """``enc_out`` (extension): encoder outputs [B, T', H] computed by the caller (the MBR step shares them with the
+        training forward); ``x`` is then ignored."""
         m, Kb, V, blk = self.model, self.beam_size, self.model.fc2.weight.shape[0], self.blk
-        dev = x.device
-        assert x.is_cuda, "pika_b200 decodes on the GPU (there is no CPU fallback)"
-        enc = engine.encoder_forward_act(m.encoder, x).contiguous()              # [B, T', H]
+        dev = x.device if enc_out is None else enc_out.device
+        assert dev.type == "cuda", "pika_b200 decodes on the GPU (there is no CPU fallback)"
+        if enc_out is None:
+            enc = engine.encoder_forward_act(m.encoder, x).contiguous()          # [B, T', H]
+        else:
+            enc = engine._to_act(enc_out)
         B, Tenc, H = enc.shape
         rows = B * Kb
         adt = enc.dtype

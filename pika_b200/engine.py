@@ -214,7 +214,11 @@ class LinearFn(torch.autograd.Function):
     """y = dropout(act(x W^T + b)) + residual; W = row-concatenation of ``weights``."""
 
     @staticmethod
-    def forward(ctx, x, residual, act, drop_p, seed, nw, *params):
+    def forward(ctx, x, residual, act, drop_p, seed, nw, premasked, mask_input_scale, *params):
+        # premasked: the incoming gradient is already d(pre-activation) -- the consumer's backward applied this layer's
+        #   ReLU(+dropout) mask (BatchNorm backward with relu_mask, or the next Linear's dgrad epilogue), so no mask pass runs here.
+        # mask_input_scale (> 0): this layer's INPUT x is relu(+dropout) output of the previous Linear; its dgrad epilogue
+        #   multiplies dx by (x != 0) * scale, i.e. hands the previous layer d(pre-activation) directly (AUX_MASK_NZ).
         weights = list(params[:nw])
         biases = list(params[nw:]) if len(params) > nw else None
         M, Kd = x.shape
@@ -226,6 +230,7 @@ class LinearFn(torch.autograd.Function):
         gemm_parts([a_parts], [w_parts], y, bias=bias, act=K.ACT_RELU if act else K.ACT_NONE, drop_p=drop_p,
                    drop_seed=seed, aux=residual, aux_mode=K.AUX_ADD if residual is not None else K.AUX_NONE)
         ctx.weights, ctx.biases, ctx.act, ctx.drop_p, ctx.seed = weights, biases, act, drop_p, seed
+        ctx.premasked, ctx.mask_input_scale = premasked, mask_input_scale
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, y if act else None)
         ctx.a_parts, ctx.w_parts = a_parts, w_parts
@@ -236,7 +241,9 @@ class LinearFn(torch.autograd.Function):
         x, y = ctx.saved_tensors
         dy = dy.contiguous()
         M, N = dy.shape
-        if ctx.act:
+        if ctx.premasked:
+            dpre = dy
+        elif ctx.act:
             dpre = torch.empty_like(dy)
             K.mask_nz(dy, y, dpre, 1.0 / (1.0 - ctx.drop_p) if ctx.drop_p > 0 else 1.0)
         elif ctx.drop_p > 0:
@@ -249,7 +256,10 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             wb, wmn = dgrad_b(ctx.w_parts)
-            gemm_parts([d_parts], [wb], dx, b_mn=wmn)
+            if ctx.mask_input_scale > 0:
+                gemm_parts([d_parts], [wb], dx, b_mn=wmn, aux=x, aux_mode=K.AUX_MASK_NZ, aux_scale=ctx.mask_input_scale)
+            else:
+                gemm_parts([d_parts], [wb], dx, b_mn=wmn)
             if dx.shape[1] != x.shape[1]:
                 dx = dx[:, :x.shape[1]]
         # dW_i = dpre[:, rows_i]^T x ; db_i = colsum(dpre)[rows_i]
@@ -266,15 +276,17 @@ class LinearFn(torch.autograd.Function):
                 grad_of(ctx.biases[i]).copy_(dbias[r:r + n_i])
             r += n_i
         n_par = len(ctx.weights) + (len(ctx.biases) if ctx.biases is not None else 0)
-        return (dx, (dy if ctx.has_res else None), None, None, None, None) + (None,) * n_par
+        return (dx, (dy if ctx.has_res else None), None, None, None, None, None, None) + (None,) * n_par
 
 
-def linear(x, weights, biases=None, act=False, drop_p=0.0, residual=None):
+def linear(x, weights, biases=None, act=False, drop_p=0.0, residual=None, premasked=False, mask_input_scale=0.0):
     weights = list(weights) if isinstance(weights, (list, tuple)) else [weights]
     if biases is not None and not isinstance(biases, (list, tuple)):
         biases = [biases]
     params = weights + (list(biases) if biases is not None else [])
-    return LinearFn.apply(x, residual, act, drop_p, _next_seed() if drop_p > 0 else 0, len(weights), *params)
+    if x.dtype != torch.bfloat16 or x.shape[1] % 8 != 0:
+        mask_input_scale = 0.0                 # the epilogue mask reads x as a 16-byte-aligned aux operand of the activation dtype
+    return LinearFn.apply(x, residual, act, drop_p, _next_seed() if drop_p > 0 else 0, len(weights), premasked, mask_input_scale, *params)
 
 
 class TdnnFn(torch.autograd.Function):
@@ -282,8 +294,9 @@ class TdnnFn(torch.autograd.Function):
     taps over strided views (trainer/model/rnnt_tdnn_transformer.py:44-59, 81-82)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, dil, stride):
+    def forward(ctx, x, weight, bias, dil, stride, premasked=False):
         B, T, C = x.shape
+        ctx.premasked = premasked
         N = weight.shape[0]
         t_out = (T - 2 * dil - 1) // stride + 1
         w_parts = stage_weight(weight)                 # [N, 3*C] row-major == weight[:, 0, k, :] at cols k*C
@@ -305,8 +318,11 @@ class TdnnFn(torch.autograd.Function):
         B, T, C = x.shape
         N = ctx.weight.shape[0]
         dil, stride, t_out = ctx.dil, ctx.stride, ctx.t_out
-        dpre = torch.empty_like(y)
-        K.mask_nz(dy.contiguous(), y, dpre, 1.0)
+        if ctx.premasked:
+            dpre = dy.contiguous()                  # BatchNormFn.backward already masked by (y > 0)
+        else:
+            dpre = torch.empty_like(y)
+            K.mask_nz(dy.contiguous(), y, dpre, 1.0)
         d_parts = stage_act(dpre)
         b_taps, wmn = [], True
         for k in range(3):
@@ -333,12 +349,14 @@ class TdnnFn(torch.autograd.Function):
             gemm_parts([d_parts], [xt], gw[:, k * C:(k + 1) * C], a_mn=True, b_mn=True, a_sel=(K.SEL_KZ, K.SEL_ZERO),
                        b_sel=(K.SEL_KZ, K.SEL_ZERO), kz_count=B)
         K.colsum(dpre.view(B * t_out, N), grad_of(ctx.bias))
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
 class BatchNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, bn, train, _w=None, _b=None):
+    def forward(ctx, x, bn, train, _w=None, _b=None, relu_input=False):
+        # relu_input: x is a ReLU output whose producer was told ``premasked``; backward returns d(pre-ReLU) = dx * (x > 0)
+        ctx.relu_input = relu_input
         rows, C = x.shape
         y = torch.empty_like(x)
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
@@ -356,9 +374,9 @@ class BatchNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, mean, rstd = ctx.saved_tensors
         dx = torch.empty_like(x)
-        K.bn_bwd(dy.contiguous(), x, dx, ctx.bn.weight.detach(), mean, rstd, ctx.train, False, grad_of(ctx.bn.weight),
+        K.bn_bwd(dy.contiguous(), x, dx, ctx.bn.weight.detach(), mean, rstd, ctx.train, ctx.relu_input, grad_of(ctx.bn.weight),
                  grad_of(ctx.bn.bias))
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -382,6 +400,7 @@ class LayerNormFn(torch.autograd.Function):
 
 
 _FUSED_ATTN = os.environ.get("PK_FUSED_ATTN", "1") != "0"
+_FOLD_MASKS = os.environ.get("PK_FOLD_MASKS", "1") != "0"
 
 
 class AttentionFn(torch.autograd.Function):
@@ -398,7 +417,7 @@ class AttentionFn(torch.autograd.Function):
             # scores / probabilities never leave the SM (pika_b200/csrc/attention.cu)
             qkv = qkv.contiguous()
             out = _new((B, T, D), like=qkv)
-            lse = torch.empty(B * heads * T, dtype=torch.float32, device=qkv.device)
+            lse = torch.empty(B * heads * K.attention_lse_stride(T), dtype=torch.float32, device=qkv.device)
             alpha = 1.0 / math.sqrt(dh)
             K.attention_fwd(qkv, out, lse, heads, alpha, drop_p, seed)
             ctx.save_for_backward(qkv, out, lse)
@@ -603,7 +622,7 @@ def _joint_forward(enc, pred, model, want_lse=False):
     h_parts = stage_act(h)
     row_lse = None
     if want_lse and _FUSED_LSE and logits.dtype == torch.bfloat16 and V % 8 == 0:
-        row_lse = torch.empty((V + 255) // 256, R, 2, dtype=torch.float32, device=enc.device)
+        row_lse = torch.empty(K.row_lse_parts(R, V, 256), R, 2, dtype=torch.float32, device=enc.device)
     gemm_parts([h_parts], [w2], logits.view(R, ldv)[:, :V], bias=fc2.bias.detach(), row_lse=row_lse,
                **({"block_n": 256} if row_lse is not None else {}))
     state = dict(row_lse=row_lse, ex=ex, py=py, h_parts=h_parts, enc_parts=enc_parts, pred_parts=pred_parts, wx=wx, w2=w2, dims=(B, T, U1, H, V, ldv))
@@ -776,8 +795,11 @@ def transformer_layer(layer, x2, B, T, training):
     ctxv = AttentionFn.apply(qkv.view(B, T, -1), att.head_count, p, _next_seed() if p > 0 else 0)
     h1 = linear(ctxv.view(B * T, -1), att.final_linear.weight, att.final_linear.bias, drop_p=p, residual=x2)
     ln2 = LayerNormFn.apply(h1, ff.layer_norm, ff.layer_norm.weight, ff.layer_norm.bias)
-    inter = linear(ln2, ff.w_1.weight, ff.w_1.bias, act=True, drop_p=p)
-    return linear(inter, ff.w_2.weight, ff.w_2.bias, drop_p=p, residual=h1)
+    fold = _FOLD_MASKS and ln2.dtype == torch.bfloat16
+    inter = linear(ln2, ff.w_1.weight, ff.w_1.bias, act=True, drop_p=p, premasked=fold)
+    # w_2's dgrad epilogue applies w_1's ReLU(+dropout) mask: inter != 0 <=> active and kept
+    return linear(inter, ff.w_2.weight, ff.w_2.bias, drop_p=p, residual=h1,
+                  mask_input_scale=(1.0 / (1.0 - p) if p > 0 else 1.0) if fold else 0.0)
 
 
 def encoder_forward_act(enc, x):
@@ -787,13 +809,14 @@ def encoder_forward_act(enc, x):
     C = enc.tdnn_nhid
     if T < 43:
         raise ValueError("encoder input has %d frames; the TDNN stack needs at least 43 (receptive field 21+1+21)" % T)
-    h = linear(_to_act(x).view(B * T, D), enc.fc_in.weight, enc.fc_in.bias, act=True)
-    h = BatchNormFn.apply(h, enc.bn_in, training, enc.bn_in.weight, enc.bn_in.bias)
+    fold = _FOLD_MASKS            # ReLU masks ride in the BatchNorm backward (pk_bn_bwd relu_mask) instead of separate passes
+    h = linear(_to_act(x).view(B * T, D), enc.fc_in.weight, enc.fc_in.bias, act=True, premasked=fold)
+    h = BatchNormFn.apply(h, enc.bn_in, training, enc.bn_in.weight, enc.bn_in.bias, fold)
     for l, (conv, bn) in enumerate(zip(enc.hidden_conv, enc.hidden_bn)):
         dil, stride = enc.TDNN_DIL_STRIDE[l]
-        h3 = TdnnFn.apply(h.view(B, T, C), conv.weight, conv.bias, dil, stride)
+        h3 = TdnnFn.apply(h.view(B, T, C), conv.weight, conv.bias, dil, stride, fold)
         T = h3.shape[1]
-        h = BatchNormFn.apply(h3.view(B * T, C), bn, training, bn.weight, bn.bias)
+        h = BatchNormFn.apply(h3.view(B * T, C), bn, training, bn.weight, bn.bias, fold)
         if (l + 1) % 3 == 0:
             h = transformer_layer(enc.transformer[l // 3], h, B, T, training)
     h = BatchNormFn.apply(h, enc.bn_final, training, enc.bn_final.weight, enc.bn_final.bias)

@@ -90,13 +90,17 @@ def gemm(a, b, c, a_mn=False, b_mn=False, a_sel=(SEL_ZB0, SEL_ZB1), b_sel=(SEL_Z
     d.k_splits = k_splits
     d.two_sm = two_sm
     if row_lse is not None:
-        bn = block_n or (64 if c.shape[-1] <= 64 else (128 if c.shape[-1] <= 128 else 256))
-        assert row_lse.dtype == torch.float32 and row_lse.is_contiguous()
-        assert tuple(row_lse.shape) == ((c.shape[-1] + bn - 1) // bn, c.shape[-2], 2) and c.dim() == 2
+        assert row_lse.dtype == torch.float32 and row_lse.is_contiguous() and c.dim() == 2
+        assert tuple(row_lse.shape) == (row_lse_parts(c.shape[-2], c.shape[-1], block_n, two_sm), c.shape[-2], 2)
         d.row_lse = row_lse.data_ptr()
-        d.two_sm = -1
     check(lib.pk_gemm_bf16(ctypes.byref(d), _stream()), "pk_gemm_bf16")
     return c
+
+
+def row_lse_parts(M, N, block_n=0, two_sm=0):
+    """number of per-row (max, sum-exp) partials the GEMM writes into ``row_lse`` for an [M, N] output: one per 256-wide
+    N tile, two when the CTA-pair kernel (two epilogue groups per tile) runs it"""
+    return int(lib.pk_gemm_row_lse_parts(M, N, block_n, two_sm))
 
 
 def rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=None, grad_scale=None, dlogits=None, want_grad=True, colsum=None,
@@ -155,12 +159,17 @@ def transpose_bf16(src, dst):
           "pk_transpose_bf16")
 
 
+def attention_lse_stride(T):
+    """row pitch of the per-(batch, head) lse / D vectors (64-element aligned so that tiles of them are bulk-copy sources)"""
+    return int(lib.pk_attention_lse_stride(T))
+
+
 def attention_fwd(qkv, out, lse, heads, alpha, drop_p=0.0, seed=0):
     """qkv [B,T,3D] bf16 (q | k | v column blocks) -> out [B,T,D], lse [B*heads*T] f32 (fused attention, head dim 64)"""
     B, T, D3 = qkv.shape
     D = D3 // 3
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and out.is_contiguous() and out.shape == (B, T, D)
-    assert lse.dtype == torch.float32 and lse.numel() == B * heads * T
+    assert lse.dtype == torch.float32 and lse.numel() == B * heads * attention_lse_stride(T)
     base, es = qkv.data_ptr(), 2
     vp = ctypes.c_void_p
     check(lib.pk_attention_fwd(vp(base), vp(base + D * es), vp(base + 2 * D * es), _L(D3), _P(out), _L(D), _P(lse), _I(B), _I(T),
@@ -171,7 +180,7 @@ def attention_bwd(qkv, out, dout, lse, dqkv, heads, alpha, drop_p=0.0, seed=0):
     B, T, D3 = qkv.shape
     D = D3 // 3
     assert dout.is_contiguous() and dqkv.is_contiguous() and dqkv.shape == qkv.shape and dout.dtype == torch.bfloat16
-    ws = torch.empty(B * heads * T, dtype=torch.float32, device=qkv.device)
+    ws = torch.empty(B * heads * attention_lse_stride(T), dtype=torch.float32, device=qkv.device)
     base, gb, es = qkv.data_ptr(), dqkv.data_ptr(), 2
     vp = ctypes.c_void_p
     check(lib.pk_attention_bwd(vp(base), vp(base + D * es), vp(base + 2 * D * es), _L(D3), _P(out), _L(D), _P(dout), _L(D), _P(lse), _P(ws),

@@ -4,7 +4,7 @@ attribute names (encoder.fc_out, embed, decoder, fc1, fc_gate, fc2)."""
 import torch
 
 
-def decode_fixture_reinit(m, blank_bias=5.0, s_l=0.15, s_hh=0.04, s_j=0.05, s_o=0.1, enc_scale=8.0, seed=2024):
+def decode_fixture_reinit(m, blank_bias=5.0, s_l=0.15, s_hh=0.04, s_j=0.05, s_o=0.1, enc_scale=8.0, seed=2024, pred_scale=1.0):
     """A randomly initialised transducer never emits blank and its prediction net barely reacts to
     its input, which makes beam search degenerate.  Re-draw the prediction
     net / joint weights from wider seeded normals and bias blank so that hypotheses mix blanks,
@@ -26,6 +26,12 @@ def decode_fixture_reinit(m, blank_bias=5.0, s_l=0.15, s_hh=0.04, s_j=0.05, s_o=
             l.weight.normal_(0, s_j, generator=gg)
         m.fc2.weight.normal_(0, s_o, generator=gg)
         m.fc2.bias[0] += blank_bias
+        if pred_scale != 1.0:
+            # weaken the prediction net's pull on the joint (its columns of fc1 / fc_gate): at V = 6000 the default draw is
+            # bistable -- all blanks, or a label run-away that ends at max_len with score gaps of 1e-3
+            H = m.fc1.weight.shape[1] // 2
+            m.fc1.weight[:, H:] *= pred_scale
+            m.fc_gate.weight[:, H:] *= pred_scale
     return m
 
 

@@ -182,17 +182,21 @@ def test_gemm_split_bf16_fp32_class():
     assert rel(c, ref) < 3e-5
 
 
-@pytest.mark.parametrize("mnk", [(300, 6000, 256), (128, 256, 64), (1000, 520, 192)])
-def test_gemm_row_lse_partials(mnk):
-    """pk_gemm_desc.row_lse: per-row, per-N-tile (max*log2e, sum 2^(x*log2e-max)) of the ROUNDED bf16 outputs."""
+@pytest.mark.parametrize("two_sm", [-1, 1])
+@pytest.mark.parametrize("mnk", [(300, 6000, 256), (128, 256, 64), (1000, 520, 192), (2049, 6000, 128)])
+def test_gemm_row_lse_partials(mnk, two_sm):
+    """pk_gemm_desc.row_lse: per-row, per-column-group (max*log2e, sum 2^(x*log2e-max)) of the ROUNDED bf16 outputs: one group per
+    256-wide N tile on the single-CTA kernel, two (128 columns each) on the CTA-pair kernel."""
     import math
     M, N, Kd = mnk
     a, b = rnd(M, Kd, seed=11, scale=0.5), rnd(N, Kd, seed=12, scale=0.5)
     bias = torch.randn(N, device="cuda")
     c = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    nt = (N + 255) // 256
+    nt = K().row_lse_parts(M, N, 256, two_sm)
+    gw = 256 * ((N + 255) // 256) // nt                 # columns per group
+    assert nt == ((N + 255) // 256) * (2 if (two_sm == 1 and M > 128) else 1)
     parts = torch.full((nt, M, 2), float("nan"), device="cuda")
-    K().gemm(a, b, c, bias=bias, block_n=256, row_lse=parts)
+    K().gemm(a, b, c, bias=bias, block_n=256, row_lse=parts, two_sm=two_sm)
     ref = a.float() @ b.float().t() + bias
     assert rel(c, ref) < 4e-3
     m = parts[:, :, 0].max(0).values
@@ -202,7 +206,10 @@ def test_gemm_row_lse_partials(mnk):
     assert (lse - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
     # every tile's partial alone equals the log-sum-exp of its own column block
     for i in range(nt):
-        blk = c[:, i * 256:(i + 1) * 256].float()
+        blk = c[:, i * gw:(i + 1) * gw].float()
+        if blk.shape[1] == 0:                              # a group entirely beyond N: the empty partial (max = -inf, sum = 0)
+            assert bool((parts[i, :, 1] == 0).all())
+            continue
         got = (parts[i, :, 0] + torch.log2(parts[i, :, 1])) * math.log(2.0)
         assert (got - torch.logsumexp(blk, -1)).abs().max().item() < 1e-4
 
@@ -227,3 +234,43 @@ def test_gemm_split_k(mnk, a_mn, b_mn, ks):
     c = torch.full((M, N), float("nan"), device="cuda")
     K().gemm(a, b, c, a_mn=bool(a_mn), b_mn=bool(b_mn), k_splits=1)          # forced off: same answer
     assert rel(c, ref) < 2e-5
+
+
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("mnk", [(304, 520, 136), (2048, 1024, 1024), (136, 256, 64), (1000, 264, 200)])
+def test_gemm_cta_pair_kernel(mnk, a_mn, b_mn, cdt):
+    """the cta_group::2 flavour (256 x 256 tile per CTA pair, two epilogue groups) on every operand layout, incl. ragged M / N
+    (the second CTA of the last pair may own no rows at all)"""
+    M, N, Kd = mnk
+    a = rnd(Kd, M, seed=21) if a_mn else rnd(M, Kd, seed=21)
+    b = rnd(Kd, N, seed=22) if b_mn else rnd(N, Kd, seed=22)
+    c = torch.full((M, N), float("nan"), device="cuda", dtype=cdt)
+    bias = torch.randn(N, device="cuda")
+    K().gemm(a, b, c, a_mn=a_mn, b_mn=b_mn, bias=bias, block_n=256, two_sm=1)
+    af = a.float().t() if a_mn else a.float()
+    bf = b.float().t() if b_mn else b.float()
+    assert rel(c, af @ bf.t() + bias) < (2e-5 if cdt == torch.float32 else 4e-3)
+
+
+def test_gemm_cta_pair_split_k_taps_and_full_epilogue():
+    """CTA-pair kernel: split-K with reduce-add, three accumulated taps with row offsets, dropout + residual epilogue"""
+    M, N, Kd = 6000, 1024, 4000
+    a, b = rnd(Kd, M, seed=31, scale=0.3), rnd(Kd, N, seed=32, scale=0.3)
+    c = torch.full((M, N), float("nan"), device="cuda")
+    K().gemm(a, b, c, a_mn=True, b_mn=True, two_sm=1, block_n=256, k_splits=3)
+    assert rel(c, a.float().t() @ b.float()) < 2e-5
+    # taps: y[t] = sum_k x[t + k] W_k^T
+    T, C, Nn = 700, 128, 512
+    x = rnd(T + 2, C, seed=33)
+    w = [rnd(Nn, C, seed=40 + k) for k in range(3)]
+    y = torch.empty(T, Nn, device="cuda")
+    K().gemm([x[k:k + T] for k in range(3)], w, y, two_sm=1, block_n=256)
+    ref = sum(x[k:k + T].float() @ w[k].float().t() for k in range(3))
+    assert rel(y, ref) < 2e-5
+    res = rnd(T, Nn, seed=50)
+    y1 = torch.empty(T, Nn, device="cuda", dtype=torch.bfloat16)
+    y2 = torch.empty(T, Nn, device="cuda", dtype=torch.bfloat16)
+    for out, two in ((y1, 1), (y2, -1)):
+        K().gemm(x[:T], w[0], out, two_sm=two, block_n=256, drop_p=0.2, drop_seed=99, aux=res, aux_mode=K().AUX_ADD, act=K().ACT_RELU)
+    assert torch.equal(y1, y2)          # same counter-based mask, same arithmetic per element on both flavours

@@ -82,7 +82,7 @@ def test_sgd_nesterov_clip_matches_oracle_and_torch(n, clip):
         topt.step()
         # same fp32 expressions; fused multiply-adds on the device differ from numpy's separate roundings by <= 1 ulp of |p|
         np.testing.assert_allclose(p_dev.cpu().numpy(), p_ref, rtol=0, atol=2e-7 * max(1.0, float(np.abs(p_ref).max())))
-        np.testing.assert_allclose(buf_dev.cpu().numpy(), buf_ref, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(buf_dev.cpu().numpy(), buf_ref, rtol=1e-6, atol=3e-7)     # fused multiply-add vs two roundings near cancellation
         np.testing.assert_allclose(p_dev.cpu().numpy(), tp.detach().numpy(), rtol=0, atol=2e-7 * max(1.0, float(np.abs(p_ref).max())))
 
 
