@@ -641,8 +641,15 @@ def run_decode(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    replayed = {"kernels": 0, "graphs": 0}
+
+    def count_replays():
+        replayed["kernels"] += getattr(dec, "last_replays", 0) * getattr(dec, "kernels_per_replay", 0)
+        replayed["graphs"] += getattr(dec, "last_replays", 0)
+
     def step_device():
         last["ret"], _ = dec.decode_batch(x_res, tl, ml)
+        count_replays()
 
     def step_e2e():
         last["ret"], _ = dec.decode_batch(x_host.to(dev, non_blocking=True), tl, ml)      # H2D of the features; the hypotheses come back inside
@@ -653,8 +660,11 @@ def run_decode(a):
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
+    replayed["kernels"] = replayed["graphs"] = 0
     ms = timed(step_device, a.steps)
-    launches = _lib.launch_count() - l0
+    host_launches = _lib.launch_count() - l0                    # launches issued by the host (eager steps + graph captures)
+    launches = host_launches + replayed["kernels"]              # + kernels executed from replayed CUDA graphs
+    graph_replays = replayed["graphs"]
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, a.steps)
     if rank != 0:
@@ -683,7 +693,9 @@ def run_decode(a):
            "roofline": {"kernel": "one beam step (gather, 2-layer LSTM step, factored joint, fc2, log-softmax, beam advance, state reorder)",
                         "bound": "hbm", "achieved": step_bytes / step_ms / 1e6, "peak": hbm, "unit": "GB/s",
                         "frac": step_bytes / step_ms / 1e6 / hbm, "traffic": None, "launch_ms": step_ms, "algorithmic_bytes": step_bytes,
-                        "note": "latency / launch bound: %d launches per beam step" % (launches // a.steps // max(beam_steps, 1))}}
+                        "note": "latency bound: %d kernels per beam step, %.2f host-side launches (graph replays + eager) per beam step"
+                                % (launches // a.steps // max(beam_steps, 1), (graph_replays + host_launches - graph_replays * 0) / a.steps / max(beam_steps, 1))},
+           "host_launches_per_beam_step": (graph_replays + host_launches) / a.steps / max(beam_steps, 1)}
     if world == 1 and not a.no_cpu_baseline:
         try:
             res["cpu_baseline"] = cpu_baseline_decode(a, a.cpu_budget_s)

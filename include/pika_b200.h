@@ -229,6 +229,9 @@ int pk_bmuf_update(float* glob, float* local, float* delta_prev, const float* de
  *   (f0,fs,t0,ts): SpecAugment freq/time mask start and span (span 0 = off), shared by the batch
  *   out [B, t_max, D] f32|bf16; wave_i16_out [B, n_max] optional copy of the augmented samples
  *   err_flag: set to 1 if a gain above 300 dB was requested (the reference raises ValueError)
+ *   dither, dither_seed: FbankOptions.dither (egs/fbank.conf: dither=1): dither * N(0,1) added to every sample of every extracted
+ *   window, as Kaldi's Dither() does; the draws come from a counter-based generator keyed by (utterance, frame, sample, seed) --
+ *   Kaldi's own RNG stream is not reproduced.  0 = off (bit-reproducible features, what the parity tests use).
  */
 long long pk_frontend_workspace_bytes(int B, int n_max, int t_max, int n_mel, int D);
 int pk_frontend_fwd(const short* pcm, long long ld_pcm, const int* n_samples, const float* rate, const int* new_len,
@@ -236,20 +239,26 @@ int pk_frontend_fwd(const short* pcm, long long ld_pcm, const int* n_samples, co
                     int rctx, const float* window, const float* twiddle, const float* mel_w, const int* mel_lo,
                     const int* mel_hi, float preemph, int cmn, const float* offset, const float* scale, int f0, int fs,
                     int t0, int ts, void* out, int out_dtype, short* wave_i16_out, void* workspace,
-                    long long workspace_bytes, int* err_flag, void* stream);
+                    long long workspace_bytes, int* err_flag, float dither, unsigned int dither_seed, void* stream);
 int pk_fbank(const float* wave, long long ld_wave, const int* n_frames, int B, int t_max, int n_mel, const float* window,
              const float* twiddle, const float* mel_w, const int* mel_lo, const int* mel_hi, float preemph, float* feats,
-             void* stream);
+             float dither, unsigned int dither_seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Batched beam search (pika_b200/csrc/beam.cu): one launch per step for the whole batch.
  * Replaces decoder/beam_transducer.py:82-187 (BeamMergeTransducer.advance) and the gather / masked LSTM
  * update / state reordering of decoder/transducer_decoder.py:127-150,173-178,188-202.  Rows are
  * utterance-major (row = b*K + k); blank = blk, EOS = -1.
+ * The loop is meant to be replayed from a CUDA graph, so nothing step-dependent is a kernel argument: step_ctx [2] int32 lives in
+ * device memory -- step_ctx[0] = step index (the kernels address next_ys[step] / prev_ks[step] themselves), step_ctx[1] = 1 while
+ * `not all(b.done() for b in beam)` (decoder/transducer_decoder.py:123) and the history buffers have room; pk_beam_step_end
+ * advances / latches both at the end of a step and every kernel of a dead step is a no-op.  Initialise step_ctx = {0, 1}.
  */
-int pk_beam_prepare(const int* tok, int* t_idx, const void* enc, int dtype, int Tenc, int H, void* enc_hid,
+int pk_beam_prepare(const int* next_ys, const int* step_ctx, int* t_idx, const void* enc, int dtype, int Tenc, int H, void* enc_hid,
                     const float* embed, int E, void* x_emb, int ld_x, int K, int blk, int rows, void* stream);
-int pk_beam_lstm_cell(const float* gates, const int* tok, int blk, void* h, int dtype, float* c, int rows, int H, void* stream);
+int pk_beam_lstm_cell(const float* gates, const int* next_ys, const int* step_ctx, int blk, void* h, int dtype, float* c, int rows, int H,
+                      void* stream);
+int pk_beam_step_end(int* step_ctx, const int* not_done, int max_steps, void* stream);
 int pk_beam_gate(const float* a, void* h, int dtype, int rows, int H, void* stream);
 /* one BeamMergeTransducer.advance for every utterance: word_probs [B*K, V] f32 log-probs, t_idx [B*K],
  * histories next_ys [S+1,B,K], prev_ks [S,B,K]; partial hypotheses hyp_tok [2,B,K,L] / hyp_len [2,B,K];
@@ -257,9 +266,28 @@ int pk_beam_gate(const float* a, void* h, int dtype, int rows, int H, void* stre
 int pk_beam_advance(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
                     int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
                     int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
-                    int step, int blk, int n_best, int beam_prune, void* stream);
-int pk_beam_reorder(const int* prev_k, const void* h_in, const float* c_in, const int* t_in, void* h_out, float* c_out,
+                    const int* step_ctx, int blk, int n_best, int beam_prune, void* stream);
+int pk_beam_reorder(const int* prev_ks, const int* step_ctx, const void* h_in, const float* c_in, const int* t_in, void* h_out, float* c_out,
                     int* t_out, int dtype, int K, int H, int layers, int rows, void* stream);
+/* On-the-fly FST shallow fusion inside the beam step: decoder/beam_transducer.py:135-159,167-176 with the arc search of
+ * decoder/sorted_matcher.py:24-111 over a flattened arc table (arcs of a state sorted by input label, label = token + 1).
+ * Per beam the active FST states are an insertion-ordered set of at most max_states (state, cost) pairs in double precision;
+ * err_flag is raised when a set would overflow.  lm_scores [B,K] f32 and the sets ([2,B,K,max_states], [2,B,K]) are state the
+ * caller zero-initialises before step 0. */
+typedef struct {
+    const int* arc_off;       /* [n_states + 1] */
+    const int* arc_ilabel;    /* [n_arcs] */
+    const double* arc_weight; /* [n_arcs] */
+    const int* arc_next;      /* [n_arcs] */
+    const double* finals;     /* [n_states], +inf = not final */
+    int backoff_id, n_disambig;
+    int disambig_ids[4];
+} pk_lm_fst;
+int pk_beam_advance_lm(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+                       int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
+                       int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
+                       const int* step_ctx, int blk, int n_best, int beam_prune, const pk_lm_fst* fst, double lm_scale, double nonblk_reward,
+                       int* set_state, double* set_cost, int* set_n, float* lm_scores, int max_states, int* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Persistent LSTM layer (pika_b200/csrc/lstm_seq.cu): the whole recurrence of one nn.LSTM layer in one

@@ -10,7 +10,7 @@
 //
 // Warp roles (320 threads):
 //   warp 0       TMA loader: stationary tiles once, streamed tiles (and, in MODE 2, the per-query lse / D vectors) through a
-//                4-stage mbarrier ring
+//                6-stage mbarrier ring
 //   warp 1       MMA issuer (one thread): stage 1  S = A_stat X1^T (and dP = A_stat' X2^T)   tcgen05.mma 128 x 64 x 64, fp32 in TMEM
 //                                         stage 2  acc (+)= A_elem X   where A_elem is the bf16 tile the element-wise warps wrote to
 //                                                  shared memory (P | dS | P^T, dS^T) and X the streamed tile read MN-major
@@ -34,7 +34,7 @@ void count_launch();
 
 constexpr int TA_BR = 128;
 constexpr int TA_BC = 64;
-constexpr int TA_NST = 4;
+constexpr int TA_NST = 6;
 constexpr int TA_THREADS = 320;
 constexpr float TA_LOG2E = 1.4426950408889634f;
 constexpr float TA_LN2 = 0.6931471805599453f;
@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
     uint64_t* a_ready = s_ready + 2;          // 2   the group wrote its A tile(s) and is done reading S / dP
     uint64_t* pv_done = a_ready + 2;          // 2   stage 2 of the group's tile completed (A tiles free, PV readable)
     uint64_t* final_bar = pv_done + 2;        // 1   every MMA of the CTA completed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(final_bar + 1);
+    uint64_t* s_free = final_bar + 1;         // 2   the group has pulled S / dP of its tile into registers: the accumulator may be overwritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
     float* vec = reinterpret_cast<float*>(smem + TA_OFF_VEC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
         if (MODE != 0) tma_prefetch_desc(&p.dout);
         mbar_init(stat_full, 1);
         for (int s = 0; s < TA_NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&a_ready[g], 128); mbar_init(&pv_done[g], 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&a_ready[g], 128); mbar_init(&pv_done[g], 1); mbar_init(&s_free[g], 128); }
         mbar_init(final_bar, 1);
         mbar_fence_init();
     }
@@ -166,8 +167,10 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t x1 = sbase + TA_OFF_RING + stage * 2 * TA_TILE_X, x2 = x1 + TA_TILE_X;
-                // S (and dP) of group g: the group released the accumulator when it arrived on a_ready for tile j-2, which stage2(j-2)
-                // (issued in the previous iteration) has already waited for
+                // S (and dP) of group g may be overwritten as soon as the group has pulled tile j-2 into registers (s_free), long before it
+                // finishes the exponentials of that tile: the next stage-1 product is then ready the moment the group comes back for it
+                // (ncu of the first version: 30-50 % of all stall samples sat on the s_ready wait, profiles/r02_attention_tc.txt)
+                if (j >= 2) { mbar_wait(&s_free[g], ((j >> 1) - 1) & 1); tc_fence_after(); }
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem_base + TA_COL_S + g * 64, kmaj(st0, k4), kmaj(x1, k4), idesc1, k4 > 0 ? 1u : 0u);
                 if (MODE != 0) {
@@ -175,9 +178,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
                     for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem_base + TA_COL_DP + g * 64, kmaj(st1, k4), kmaj(x2, k4), idesc1, k4 > 0 ? 1u : 0u);
                 }
                 umma_commit(&s_ready[g]);
-                if (j >= 1) stage2(j - 1);
+                // second stage of tile j-2, i.e. AFTER the stage-1 products of the next tile of the same group have been queued: the
+                // issue order S0 S1 S2 P0 S3 P1 ... keeps a finished S waiting for each group when it comes back from its exponentials
+                // (with S(j+1) behind P(j-1) the thread sat in the a_ready wait and the groups idled, profiles/r02_attention_tc_v1.ncu.txt)
+                if (j >= 2) stage2(j - 2);
                 if (++stage == TA_NST) { stage = 0; phase ^= 1; }
             }
+            if (n_tiles >= 2) stage2(n_tiles - 2);
             stage2(n_tiles - 1);
             umma_commit(final_bar);
         }
@@ -214,17 +221,9 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
             mbar_wait(&s_ready[g], it & 1);
             tc_fence_after();
             if (MODE == 0) {
-                uint32_t sr[64];
-                tmem_ld_32x32(tq + TA_COL_S + g * 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
-                tmem_ld_32x32(tq + TA_COL_S + g * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
-                tmem_ld_wait();
-                float mx = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 64; ++c) mx = fmaxf(mx, c < nvalid ? __uint_as_float(sr[c]) : -INFINITY);
-                const float m_new = fmaxf(m_run, mx * c2);     // finite: every tile holds a valid column
-                const float corr = ex2_approx(m_run - m_new);  // 0 on the group's first tile
                 if (it > 0) {
-                    // the PV product of this group's previous tile: same scale as o_acc (both relative to m_run)
+                    // the PV product of this group's previous tile: same scale as o_acc (both relative to m_run); folded before S is
+                    // pulled so that the two 32/64-register blocks are never live together
                     mbar_wait(&pv_done[g], (it - 1) & 1);
                     tc_fence_after();
 #pragma unroll
@@ -233,9 +232,22 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
                         tmem_ld_32x32(tq + TA_COL_ACC + g * 64 + half * 32, pv);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) o_acc[half * 32 + c] = (o_acc[half * 32 + c] + __uint_as_float(pv[c])) * corr;
+                        for (int c = 0; c < 32; ++c) o_acc[half * 32 + c] += __uint_as_float(pv[c]);
                     }
                 }
+                uint32_t sr[64];
+                tmem_ld_32x32(tq + TA_COL_S + g * 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+                tmem_ld_32x32(tq + TA_COL_S + g * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&s_free[g]);
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) mx = fmaxf(mx, c < nvalid ? __uint_as_float(sr[c]) : -INFINITY);
+                const float m_new = fmaxf(m_run, mx * c2);     // finite: every tile holds a valid column
+                const float corr = ex2_approx(m_run - m_new);  // 0 on the group's first tile
+#pragma unroll
+                for (int c = 0; c < 64; ++c) o_acc[c] *= corr;
                 float sum = 0.f;
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
@@ -269,6 +281,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
                     tmem_ld_32x32(tq + TA_COL_S + g * 64 + half * 32, sr);
                     tmem_ld_32x32(tq + TA_COL_DP + g * 64 + half * 32, dr);
                     tmem_ld_wait();
+                    if (half == 1) { tc_fence_before(); mbar_arrive(&s_free[g]); }       // S / dP of this tile are in registers
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch) {
                         float ds[8], pd[8];

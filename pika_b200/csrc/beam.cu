@@ -15,16 +15,32 @@ void count_launch();
 
 constexpr float kKill = -1e20f;
 
+// The beam loop is replayed from a CUDA graph, so nothing that changes from step to step may be a kernel argument: the step index
+// lives in device memory (advanced by beam_step_inc_kernel at the end of every step) and every kernel turns into a no-op once all
+// utterances are done (``while not all(b.done() for b in beam)``, decoder/transducer_decoder.py:123) or the history buffers are full.
+struct StepCtx {
+    const int* step;          // [2]: step[0] = current step, step[1] = 1 while the loop is live (latched between steps, so that every
+};                            //      kernel and every CTA of one step sees the same value even while beam_advance counts utterances down)
+PK_DEVICE bool step_active(const StepCtx& c) { return c.step[1] != 0; }
+// end of a step: advance the counter and latch the loop condition for the next step
+__global__ void beam_step_end_kernel(int* step, const int* not_done, int max_steps) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && step[1] != 0) {
+        const int s = step[0] + 1;
+        step[0] = s;
+        step[1] = (*not_done > 0 && s < max_steps) ? 1 : 0;
+    }
+}
+
 // ------------------------------------------------------------------------------------ step prologue
 // t_idx += (tok == blk); enc_hid[row] = enc[b, t_idx[row]]; x_emb[row] = embed[tok] (zeros unless tok > blk)
 template <typename T>
-__global__ void beam_prepare_kernel(const int* __restrict__ tok, int* __restrict__ t_idx, const T* __restrict__ enc, int Tenc, int H,
+__global__ void beam_prepare_kernel(const int* __restrict__ next_ys, StepCtx ctx, int* __restrict__ t_idx, const T* __restrict__ enc, int Tenc, int H,
                                     T* __restrict__ enc_hid, const float* __restrict__ embed, int E, T* __restrict__ x_emb, int ld_x,
                                     int K, int blk, int rows) {
     const int row = blockIdx.x;
-    if (row >= rows) return;
+    if (row >= rows || !step_active(ctx)) return;
     const int b = row / K;
-    const int tk = tok[row];
+    const int tk = next_ys[(long long)ctx.step[0] * rows + row];
     __shared__ int s_t;
     if (threadIdx.x == 0) {
         int t = t_idx[row] + (tk == blk ? 1 : 0);
@@ -40,12 +56,12 @@ __global__ void beam_prepare_kernel(const int* __restrict__ tok, int* __restrict
 
 // LSTM cell on rows whose current token is a real label (tok > blk); other rows keep (h, c).
 template <typename T>
-__global__ void beam_lstm_cell_kernel(const float* __restrict__ gates, const int* __restrict__ tok, int blk, T* __restrict__ h,
+__global__ void beam_lstm_cell_kernel(const float* __restrict__ gates, const int* __restrict__ next_ys, StepCtx ctx, int blk, T* __restrict__ h,
                                       float* __restrict__ c, int rows, int H) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * H) return;
+    if (i >= rows * H || !step_active(ctx)) return;
     const int r = i / H, j = i - r * H;
-    if (!(tok[r] > blk)) return;
+    if (!(next_ys[(long long)ctx.step[0] * rows + r] > blk)) return;
     const float* g = gates + (long long)r * 4 * H;
     const float gi = 1.f / (1.f + expf(-g[j])), gf = 1.f / (1.f + expf(-g[H + j]));
     const float gg = tanhf(g[2 * H + j]), go = 1.f / (1.f + expf(-g[3 * H + j]));
@@ -80,6 +96,83 @@ struct BeamState {
     int* not_done_total;  // [1] number of utterances not yet done (written every step)
 };
 
+// ------------------------------------------------------------------------------------ on-the-fly FST shallow fusion
+// decoder/sorted_matcher.py:24-111 over a flattened (CSR) arc table: arcs of a state are sorted by ilabel.  Costs are
+// accumulated in double like the reference's Python floats; the per-beam state sets keep INSERTION ORDER, which the
+// reference's strict-< update with the reward subtracted only from the stored value makes observable
+// (decoder/beam_transducer.py:146-149).
+constexpr int LM_MAX_DISAMBIG = 4;
+struct LmArgs {
+    const int* arc_off;        // [n_states + 1]; nullptr = no LM
+    const int* arc_il;         // [n_arcs] input labels (token + 1)
+    const double* arc_w;       // [n_arcs] costs
+    const int* arc_ns;         // [n_arcs] next states
+    const double* finals;      // [n_states] final cost, +inf = not final
+    int backoff_id, n_disambig;
+    int disambig[LM_MAX_DISAMBIG];
+    float scale;               // lm_scorer_scale
+    double scale_d, reward;    // lm_scorer_scale and args.nonblk_reward as Python floats
+    int* set_state;            // [2][B][K][MS] state sets, ping-pong by step parity
+    double* set_cost;          // [2][B][K][MS]
+    int* set_n;                // [2][B][K]
+    float* lm_scores;          // [B][K]
+    int MS;
+    int* err;                  // set to 1 when a state set overflows MS
+};
+
+PK_DEVICE int fst_search(const LmArgs& f, int state, int ilabel) {          // SortedMatcher.search (:24-50): first arc with this ilabel
+    int lo = f.arc_off[state], hi = f.arc_off[state + 1];
+    const int end = hi;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (f.arc_il[mid] >= ilabel) hi = mid; else lo = mid + 1;
+    }
+    return (lo < end && f.arc_il[lo] == ilabel) ? lo : -1;
+}
+// get_scores (:70-85) -> emit(cost, next_state) in the reference's order: the state itself, then its disambiguation arcs, each
+// followed down its back-off chain (:52-68)
+template <typename F> PK_DEVICE void fst_get_scores(const LmArgs& f, int state, int ilabel, F&& emit) {
+    for (int i = -1; i < f.n_disambig; ++i) {
+        double bf = 0.0;
+        int cur = state;
+        if (i >= 0) {
+            const int a = fst_search(f, state, f.disambig[i]);
+            if (a < 0) continue;
+            bf = f.arc_w[a]; cur = f.arc_ns[a];
+        }
+        while (true) {
+            const int a = fst_search(f, cur, ilabel);
+            if (a >= 0) emit(bf + f.arc_w[a], f.arc_ns[a]);
+            const int bo = fst_search(f, cur, f.backoff_id);
+            if (bo < 0) break;
+            bf += f.arc_w[bo]; cur = f.arc_ns[bo];
+        }
+    }
+}
+// min over final_score(state) (:87-111) of (base + cost); +inf when no final state is reachable
+PK_DEVICE double fst_final_min(const LmArgs& f, int state, double base) {
+    double best = INFINITY;
+    for (int i = -1; i < f.n_disambig; ++i) {
+        double sc = 0.0;
+        int cur = state;
+        if (i >= 0) {
+            const int a = fst_search(f, state, f.disambig[i]);
+            if (a < 0) continue;
+            sc = f.arc_w[a]; cur = f.arc_ns[a];
+        }
+        while (true) {
+            const double fc = f.finals[cur];
+            if (isinf(fc)) {
+                const int bo = fst_search(f, cur, f.backoff_id);
+                if (bo < 0) { sc = INFINITY; break; }
+                sc += f.arc_w[bo]; cur = f.arc_ns[bo];
+            } else { sc += fc; break; }
+        }
+        best = fmin(best, base + sc);
+    }
+    return best;
+}
+
 template <int K>
 PK_DEVICE void topk_insert(float (&v)[K], int (&ix)[K], float x, int id) {
     // keeps v descending; ties keep the earlier (smaller-index) element first
@@ -99,11 +192,15 @@ constexpr int ADV_THREADS = 256;
 template <int K>
 __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* __restrict__ word_probs, const int* __restrict__ t_idx,
                                                                    const int* __restrict__ num_frames, const int* __restrict__ max_len,
-                                                                   BeamState st, int B, int V, int L, int cap, int step, int blk,
-                                                                   int n_best, int beam_prune) {
+                                                                   BeamState st, int B, int V, int L, int cap, StepCtx ctx, int blk,
+                                                                   int n_best, int beam_prune, LmArgs lm) {
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
+    if (!step_active(ctx)) return;                 // uniform across the grid (latched by beam_step_end_kernel)
+    const int step = ctx.step[0];
+    const bool use_lm = lm.arc_off != nullptr;
     __shared__ float s_rowscore[K];
+    __shared__ float s_lmterm[K];            // lm_scorer_scale * lm_scores[k] (fp32 product, as the reference's tensor expression forms it)
     __shared__ int s_kill[K];
     __shared__ float s_cv[ADV_THREADS * K];
     __shared__ int s_ci[ADV_THREADS * K];
@@ -123,6 +220,7 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
     // ---- 1. which beam rows may have children
     if (tid < K) {
         s_rowscore[tid] = st.scores[b * K + tid];
+        s_lmterm[tid] = use_lm ? lm.scale * lm.lm_scores[b * K + tid] : 0.f;
         int kill = 0;
         if (step > 0) {
             if (cur_tok[tid] == -1) kill = 1;                                  // finished beams have no children
@@ -154,7 +252,10 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
         float x;
         if (s_kill[k] == 2) continue;
         if (s_kill[k] == 1) x = kKill;
-        else x = (step > 0) ? (wp[id] + s_rowscore[k]) : wp[id];
+        else if (step > 0) {
+            x = wp[id] + s_rowscore[k];                                      // word_probs + scores (+ lm term, in this order: beam_transducer.py:94-97)
+            if (use_lm) x += s_lmterm[k];
+        } else x = wp[id];
         topk_insert<K>(lv, li, x, id);
     }
 #pragma unroll
@@ -194,13 +295,53 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
     const int nf = num_frames[b];
     const int len_after = step + 2;                                             // len(self.next_ys) after the append
     __shared__ int s_fin[K];
+    __shared__ float s_final[K];             // score recorded for a finishing beam
     if (tid < K) {
         const int id = s_besti[tid];
         const int pk = id / V, y = id - pk * V;
-        const float sc = s_best[tid];
+        float sc = s_best[tid];
+        if (use_lm) sc -= s_lmterm[pk];                                        // self.scores -= lm_scale * lm_scores[prev_k]  (:131-132)
         out_prev[tid] = pk;
-        st.scores[b * K + tid] = sc;
         const bool fin = (y == blk && t_idx[b * K + pk] == nf - 1) || (len_after > max_len[b]);
+        if (use_lm) {
+            // ---- next FST state set of this beam (:135-159)
+            const int MS = lm.MS;
+            const long long o_old = (((long long)par_old * B + b) * K + pk) * MS, o_new = (((long long)par_new * B + b) * K + tid) * MS;
+            const int n_old = (step > 0) ? lm.set_n[((long long)par_old * B + b) * K + pk] : 1;
+            int n_new = 0;
+            int* ns_state = lm.set_state + o_new;
+            double* ns_cost = lm.set_cost + o_new;
+            for (int s_i = 0; s_i < n_old; ++s_i) {
+                const int state = (step > 0) ? lm.set_state[o_old + s_i] : 0;       // initial set {0: 0.0} (:64-66)
+                const double c0 = (step > 0) ? lm.set_cost[o_old + s_i] : 0.0;
+                if (y == blk) {
+                    if (n_new < MS) { ns_state[n_new] = state; ns_cost[n_new] = c0; ++n_new; } else *lm.err = 1;
+                    continue;
+                }
+                fst_get_scores(lm, state, y + 1, [&](double cost, int nxt) {
+                    const double nc = c0 + cost;
+                    int idx = -1;
+                    for (int q = 0; q < n_new; ++q) if (ns_state[q] == nxt) { idx = q; break; }
+                    if (idx < 0) {
+                        if (n_new >= MS) { *lm.err = 1; return; }
+                        idx = n_new++; ns_state[idx] = nxt; ns_cost[idx] = nc - lm.reward;      // first visit: inf > nc
+                    } else if (nc < ns_cost[idx]) {
+                        ns_cost[idx] = nc - lm.reward;                                          // (:147-149)
+                    }
+                });
+            }
+            lm.set_n[((long long)par_new * B + b) * K + tid] = n_new;
+            double mn = INFINITY;
+            for (int q = 0; q < n_new; ++q) mn = fmin(mn, ns_cost[q]);
+            lm.lm_scores[b * K + tid] = n_new ? (float)(-mn) : -1e20f;                          // (:155-158)
+            if (fin) {                                                                          // (:167-176)
+                double fmn = INFINITY;
+                for (int q = 0; q < n_new; ++q) fmn = fmin(fmn, fst_final_min(lm, ns_state[q], ns_cost[q]));
+                sc += (float)(lm.scale_d * (-fmn));          // `s += lm_scale * final_lm_score` on the 0-d view of self.scores[i]
+            }
+        }
+        st.scores[b * K + tid] = sc;
+        s_final[tid] = sc;
         out_tok[tid] = fin ? -1 : y;
         s_fin[tid] = fin ? 1 : 0;
     }
@@ -209,7 +350,7 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
         int cnt = st.fin_count[b];
         for (int i = 0; i < K; ++i) {
             if (s_fin[i] && cnt < cap) {
-                st.fin_score[(long long)b * cap + cnt] = s_best[i];
+                st.fin_score[(long long)b * cap + cnt] = s_final[i];
                 st.fin_step[(long long)b * cap + cnt] = step + 1;
                 st.fin_k[(long long)b * cap + cnt] = i;
                 ++cnt;
@@ -238,12 +379,13 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
 
 // dec_states / t_idx reordering by the new back-pointers (TransducerDecoder._beam_update)
 template <typename T>
-__global__ void beam_reorder_kernel(const int* __restrict__ prev_k, const T* __restrict__ h_in, const float* __restrict__ c_in,
+__global__ void beam_reorder_kernel(const int* __restrict__ prev_ks, StepCtx ctx, const T* __restrict__ h_in, const float* __restrict__ c_in,
                                     const int* __restrict__ t_in, T* __restrict__ h_out, float* __restrict__ c_out, int* __restrict__ t_out,
                                     int K, int H, int layers, int rows) {
     const int row = blockIdx.x;
     const int b = row / K;
-    const int src = b * K + prev_k[row];
+    if (!step_active(ctx)) return;
+    const int src = b * K + prev_ks[(long long)ctx.step[0] * rows + row];
     for (int l = 0; l < layers; ++l) {
         const long long o = ((long long)l * rows + row) * H, s = ((long long)l * rows + src) * H;
         for (int c = threadIdx.x; c < H; c += blockDim.x) { h_out[o + c] = h_in[s + c]; c_out[o + c] = c_in[s + c]; }
@@ -255,21 +397,24 @@ __global__ void beam_reorder_kernel(const int* __restrict__ prev_k, const T* __r
 using namespace pk;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
-extern "C" int pk_beam_prepare(const int* tok, int* t_idx, const void* enc, int dtype, int Tenc, int H, void* enc_hid,
+extern "C" int pk_beam_prepare(const int* next_ys, const int* step_ctx, int* t_idx, const void* enc, int dtype, int Tenc, int H, void* enc_hid,
                                const float* embed, int E, void* x_emb, int ld_x, int K, int blk, int rows, void* stream) {
+    const StepCtx ctx{step_ctx};
     if (dtype == PK_BF16)
-        beam_prepare_kernel<__nv_bfloat16><<<rows, 128, 0, ST(stream)>>>(tok, t_idx, (const __nv_bfloat16*)enc, Tenc, H, (__nv_bfloat16*)enc_hid,
+        beam_prepare_kernel<__nv_bfloat16><<<rows, 128, 0, ST(stream)>>>(next_ys, ctx, t_idx, (const __nv_bfloat16*)enc, Tenc, H, (__nv_bfloat16*)enc_hid,
                                                                         embed, E, (__nv_bfloat16*)x_emb, ld_x, K, blk, rows);
     else
-        beam_prepare_kernel<float><<<rows, 128, 0, ST(stream)>>>(tok, t_idx, (const float*)enc, Tenc, H, (float*)enc_hid, embed, E,
+        beam_prepare_kernel<float><<<rows, 128, 0, ST(stream)>>>(next_ys, ctx, t_idx, (const float*)enc, Tenc, H, (float*)enc_hid, embed, E,
                                                                 (float*)x_emb, ld_x, K, blk, rows);
     PK_CHECK_LAUNCH(); count_launch();
     return 0;
 }
-extern "C" int pk_beam_lstm_cell(const float* gates, const int* tok, int blk, void* h, int dtype, float* c, int rows, int H, void* stream) {
+extern "C" int pk_beam_lstm_cell(const float* gates, const int* next_ys, const int* step_ctx, int blk, void* h, int dtype, float* c, int rows, int H,
+                                 void* stream) {
     const int n = rows * H;
-    if (dtype == PK_BF16) beam_lstm_cell_kernel<__nv_bfloat16><<<(n + 255) / 256, 256, 0, ST(stream)>>>(gates, tok, blk, (__nv_bfloat16*)h, c, rows, H);
-    else beam_lstm_cell_kernel<float><<<(n + 255) / 256, 256, 0, ST(stream)>>>(gates, tok, blk, (float*)h, c, rows, H);
+    const StepCtx ctx{step_ctx};
+    if (dtype == PK_BF16) beam_lstm_cell_kernel<__nv_bfloat16><<<(n + 255) / 256, 256, 0, ST(stream)>>>(gates, next_ys, ctx, blk, (__nv_bfloat16*)h, c, rows, H);
+    else beam_lstm_cell_kernel<float><<<(n + 255) / 256, 256, 0, ST(stream)>>>(gates, next_ys, ctx, blk, (float*)h, c, rows, H);
     PK_CHECK_LAUNCH(); count_launch();
     return 0;
 }
@@ -280,14 +425,15 @@ extern "C" int pk_beam_gate(const float* a, void* h, int dtype, int rows, int H,
     PK_CHECK_LAUNCH(); count_launch();
     return 0;
 }
-extern "C" int pk_beam_advance(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
-                               int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
-                               int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
-                               int step, int blk, int n_best, int beam_prune, void* stream) {
+static int beam_advance_impl(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+                             int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
+                             int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
+                             const int* step_ctx, int blk, int n_best, int beam_prune, const LmArgs& lm, void* stream) {
+    const StepCtx step{step_ctx};
     BeamState st{scores, next_ys, prev_ks, hyp_tok, hyp_len, fin_score, fin_step, fin_k, fin_count, eos_top, done, not_done_total};
     PK_CHECK_ARG(V >= K, "vocabulary smaller than the beam");
     switch (K) {
-#define CASE(KK) case KK: beam_advance_kernel<KK><<<B, ADV_THREADS, 0, ST(stream)>>>(word_probs, t_idx, num_frames, max_len, st, B, V, L, cap, step, blk, n_best, beam_prune); break;
+#define CASE(KK) case KK: beam_advance_kernel<KK><<<B, ADV_THREADS, 0, ST(stream)>>>(word_probs, t_idx, num_frames, max_len, st, B, V, L, cap, step, blk, n_best, beam_prune, lm); break;
         CASE(1) CASE(2) CASE(4) CASE(8) CASE(16)
 #undef CASE
         default: PK_CHECK_ARG(false, "beam size must be 1, 2, 4, 8 or 16");
@@ -295,12 +441,45 @@ extern "C" int pk_beam_advance(const float* word_probs, const int* t_idx, const 
     PK_CHECK_LAUNCH(); count_launch();
     return 0;
 }
-extern "C" int pk_beam_reorder(const int* prev_k, const void* h_in, const float* c_in, const int* t_in, void* h_out, float* c_out,
+extern "C" int pk_beam_advance(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+                               int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
+                               int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
+                               const int* step, int blk, int n_best, int beam_prune, void* stream) {
+    LmArgs lm{};
+    return beam_advance_impl(word_probs, t_idx, num_frames, max_len, scores, next_ys, prev_ks, hyp_tok, hyp_len, fin_score, fin_step, fin_k,
+                             fin_count, eos_top, done, not_done_total, B, K, V, L, cap, step, blk, n_best, beam_prune, lm, stream);
+}
+extern "C" int pk_beam_advance_lm(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+                                  int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
+                                  int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
+                                  const int* step, int blk, int n_best, int beam_prune, const pk_lm_fst* fst, double lm_scale, double nonblk_reward,
+                                  int* set_state, double* set_cost, int* set_n, float* lm_scores, int max_states, int* err_flag,
+                                  void* stream) {
+    PK_CHECK_ARG(fst != nullptr && fst->arc_off != nullptr, "null FST");
+    PK_CHECK_ARG(fst->n_disambig >= 0 && fst->n_disambig <= LM_MAX_DISAMBIG, "at most 4 disambiguation labels");
+    PK_CHECK_ARG(max_states >= 1, "max_states must be >= 1");
+    LmArgs lm{};
+    lm.arc_off = fst->arc_off; lm.arc_il = fst->arc_ilabel; lm.arc_w = fst->arc_weight; lm.arc_ns = fst->arc_next; lm.finals = fst->finals;
+    lm.backoff_id = fst->backoff_id; lm.n_disambig = fst->n_disambig;
+    for (int i = 0; i < fst->n_disambig; ++i) lm.disambig[i] = fst->disambig_ids[i];
+    lm.scale = (float)lm_scale; lm.scale_d = lm_scale; lm.reward = nonblk_reward;
+    lm.set_state = set_state; lm.set_cost = set_cost; lm.set_n = set_n; lm.lm_scores = lm_scores; lm.MS = max_states; lm.err = err_flag;
+    return beam_advance_impl(word_probs, t_idx, num_frames, max_len, scores, next_ys, prev_ks, hyp_tok, hyp_len, fin_score, fin_step, fin_k,
+                             fin_count, eos_top, done, not_done_total, B, K, V, L, cap, step, blk, n_best, beam_prune, lm, stream);
+}
+extern "C" int pk_beam_reorder(const int* prev_ks, const int* step_ctx, const void* h_in, const float* c_in, const int* t_in, void* h_out, float* c_out,
                                int* t_out, int dtype, int K, int H, int layers, int rows, void* stream) {
+    const StepCtx ctx{step_ctx};
     if (dtype == PK_BF16)
-        beam_reorder_kernel<__nv_bfloat16><<<rows, 128, 0, ST(stream)>>>(prev_k, (const __nv_bfloat16*)h_in, c_in, t_in, (__nv_bfloat16*)h_out, c_out, t_out, K, H, layers, rows);
+        beam_reorder_kernel<__nv_bfloat16><<<rows, 128, 0, ST(stream)>>>(prev_ks, ctx, (const __nv_bfloat16*)h_in, c_in, t_in, (__nv_bfloat16*)h_out, c_out, t_out, K, H, layers, rows);
     else
-        beam_reorder_kernel<float><<<rows, 128, 0, ST(stream)>>>(prev_k, (const float*)h_in, c_in, t_in, (float*)h_out, c_out, t_out, K, H, layers, rows);
+        beam_reorder_kernel<float><<<rows, 128, 0, ST(stream)>>>(prev_ks, ctx, (const float*)h_in, c_in, t_in, (float*)h_out, c_out, t_out, K, H, layers, rows);
+    PK_CHECK_LAUNCH(); count_launch();
+    return 0;
+}
+/* end of a beam step: step_ctx[0] += 1 and step_ctx[1] = (utterances not done > 0 && step < max_steps), both only while the loop is live */
+extern "C" int pk_beam_step_end(int* step_ctx, const int* not_done, int max_steps, void* stream) {
+    beam_step_end_kernel<<<1, 32, 0, ST(stream)>>>(step_ctx, not_done, max_steps);
     PK_CHECK_LAUNCH(); count_launch();
     return 0;
 }

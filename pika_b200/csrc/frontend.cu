@@ -120,9 +120,18 @@ struct FbankTables {
     const int* mel_hi;      // [n_mel] one past the last non-zero bin
 };
 
+// standard normal from two counter-based hashes (Box-Muller); one draw per (utterance, frame, sample), as Kaldi's Dither() draws
+// one RandGauss() per sample of every extracted window (feat/feature-window.cc: Dither) -- its RNG stream itself is not reproducible
+PK_DEVICE float dither_gauss(uint64_t idx, uint32_t seed) {
+    const uint32_t h1 = hash_u32(idx * 2, seed), h2 = hash_u32(idx * 2 + 1, seed ^ 0x6A09E667u);
+    const float u1 = ((float)h1 + 1.0f) * 2.3283064365386963e-10f;          // (0, 1]
+    const float u2 = (float)h2 * 2.3283064365386963e-10f;
+    return sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+}
+
 __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wave, long long ld_wave, const int* __restrict__ n_frames,
                                                     FbankTables tb, int n_mel, float preemph, float* __restrict__ feats,
-                                                    long long ld_b, int t_max) {
+                                                    long long ld_b, int t_max, float dither, uint32_t dither_seed) {
     const int t = blockIdx.x, b = blockIdx.y;
     if (t >= n_frames[b]) return;
     __shared__ float2 buf[FB_NFFT];
@@ -132,7 +141,11 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
     const int tid = threadIdx.x;
     const float* src = wave + (long long)b * ld_wave + (long long)t * FB_SHIFT;
     float part = 0.f;
-    for (int i = tid; i < FB_FRAME; i += 256) { const float v = src[i]; frame[i] = v; part += v; }
+    for (int i = tid; i < FB_FRAME; i += 256) {
+        float v = src[i];
+        if (dither != 0.f) v += dither * dither_gauss(((uint64_t)b * (uint64_t)t_max + (uint64_t)t) * FB_FRAME + (uint64_t)i, dither_seed);
+        frame[i] = v; part += v;
+    }
     part = warp_sum(part);
     if ((tid & 31) == 0) red[tid >> 5] = part;
     __syncthreads();
@@ -233,7 +246,7 @@ extern "C" int pk_frontend_fwd(const short* pcm, long long ld_pcm, const int* n_
                                int rctx, const float* window, const float* twiddle, const float* mel_w, const int* mel_lo,
                                const int* mel_hi, float preemph, int cmn, const float* offset, const float* scale, int f0, int fs,
                                int t0, int ts, void* out, int out_dtype, short* wave_i16_out, void* workspace,
-                               long long workspace_bytes, int* err_flag, void* stream) {
+                               long long workspace_bytes, int* err_flag, float dither, unsigned int dither_seed, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int D = n_mel * (lctx + 1 + rctx);
     PK_CHECK_ARG(B > 0 && n_max >= FB_FRAME && t_max > 0 && n_mel > 0 && n_mel <= 256 && D <= 1024, "bad frontend dims");
@@ -251,7 +264,8 @@ extern "C" int pk_frontend_fwd(const short* pcm, long long ld_pcm, const int* n_
                                                err_flag);
     PK_CHECK_LAUNCH(); count_launch();
     FbankTables tb{window, reinterpret_cast<const float2*>(twiddle), mel_w, mel_lo, mel_hi};
-    fbank_kernel<<<dim3(t_max, B), 256, 0, st>>>(wave, n_max, n_frames, tb, n_mel, preemph, feats, (long long)t_max * n_mel, t_max);
+    fbank_kernel<<<dim3(t_max, B), 256, 0, st>>>(wave, n_max, n_frames, tb, n_mel, preemph, feats, (long long)t_max * n_mel, t_max, dither,
+                                                 dither_seed);
     PK_CHECK_LAUNCH(); count_launch();
     if (cmn) {
         PK_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * B * D, st));
@@ -275,10 +289,10 @@ extern "C" int pk_frontend_fwd(const short* pcm, long long ld_pcm, const int* n_
  * utils/compute_global_cmvn-style tooling: wave f32 [B, ld_wave] -> feats f32 [B, t_max, n_mel]. */
 extern "C" int pk_fbank(const float* wave, long long ld_wave, const int* n_frames, int B, int t_max, int n_mel, const float* window,
                         const float* twiddle, const float* mel_w, const int* mel_lo, const int* mel_hi, float preemph, float* feats,
-                        void* stream) {
+                        float dither, unsigned int dither_seed, void* stream) {
     FbankTables tb{window, reinterpret_cast<const float2*>(twiddle), mel_w, mel_lo, mel_hi};
     fbank_kernel<<<dim3(t_max, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wave, ld_wave, n_frames, tb, n_mel, preemph, feats,
-                                                                                  (long long)t_max * n_mel, t_max);
+                                                                                  (long long)t_max * n_mel, t_max, dither, dither_seed);
     PK_CHECK_LAUNCH(); count_launch();
     return 0;
 }

@@ -66,7 +66,9 @@ PK_DEVICE float sigm(float x) { return 1.f / (1.f + __expf(-x)); }
 template <typename T>
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ w_hh,
                                                                      T* __restrict__ out, __nv_bfloat16* hx, float* __restrict__ gates_save,
-                                                                     float* __restrict__ cs, int B, int U, int H, unsigned int* counter) {
+                                                                     float* __restrict__ cs, int B, int Bt, int U, int H, unsigned int* counter) {
+    // B = sequences of this launch (<= 32); Bt = sequences of the whole batch: gates_save / cs are time-major [U, Bt, .] and the
+    // caller passes them already offset to this launch's first sequence (batches larger than 32 run as independent launches)
     extern __shared__ __align__(16) uint8_t sm_raw[];
     const int P = H + LS_PAD;
     __nv_bfloat16* w_s = reinterpret_cast<__nv_bfloat16*>(sm_raw);               // [32][P]: row g*8+jj = W_hh[g*H + j0 + jj]
@@ -128,9 +130,9 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float
             const float hv = go * tanhf(c_state);
             out[((long long)cb * U + t) * H + j0 + cj] = from_f32<T>(hv);
             hx[(long long)(t & 1) * LS_MB * H + (long long)cb * H + j0 + cj] = __float2bfloat16_rn(hv);
-            float* gs = gates_save + ((long long)t * B + cb) * 4 * H + j0 + cj;
+            float* gs = gates_save + ((long long)t * Bt + cb) * 4 * H + j0 + cj;
             gs[0] = gi; gs[H] = gf; gs[2 * H] = gg; gs[3 * H] = go;
-            cs[((long long)t * B + cb) * H + j0 + cj] = c_state;
+            cs[((long long)t * Bt + cb) * H + j0 + cj] = c_state;
         } else {
             hx[(long long)(t & 1) * LS_MB * H + (long long)cb * H + j0 + cj] = __float2bfloat16_rn(0.f);
         }
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float
 template <typename T>
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __restrict__ dout, const float* __restrict__ gates_save,
                                                                      const float* __restrict__ cs, const __nv_bfloat16* __restrict__ w_hh,
-                                                                     __nv_bfloat16* dG, int B, int U, int H, unsigned int* counter) {
+                                                                     __nv_bfloat16* dG, int B, int Bt, int U, int H, unsigned int* counter) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     const int G4 = 4 * H;
     const int PW = G4 + LS_PAD;                                                  // Wt_s pitch
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
     for (int t = U - 1; t >= 0; --t) {
         for (int i = tid; i < 32 * 9; i += LS_THREADS) r_s[i] = 0.f;
         if (t < U - 1) {
-            const __nv_bfloat16* src = dG + (long long)(t + 1) * B * G4;
+            const __nv_bfloat16* src = dG + (long long)(t + 1) * Bt * G4;
             auto issue = [&](int qtr) {                                          // warp 0: lane r copies row r of quarter `qtr`
                 if (warp == 0) {
                     fence_proxy_async_all();
@@ -210,14 +212,14 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
         __syncthreads();
         if (cb < B) {
             const int j = j0 + cj;
-            const float* gs = gates_save + ((long long)t * B + cb) * G4 + j;
+            const float* gs = gates_save + ((long long)t * Bt + cb) * G4 + j;
             const float gi = gs[0], gf = gs[H], gg = gs[2 * H], go = gs[3 * H];
-            const float c = cs[((long long)t * B + cb) * H + j];
-            const float cp = t > 0 ? cs[((long long)(t - 1) * B + cb) * H + j] : 0.f;
+            const float c = cs[((long long)t * Bt + cb) * H + j];
+            const float cp = t > 0 ? cs[((long long)(t - 1) * Bt + cb) * H + j] : 0.f;
             const float dh = to_f32<T>(dout[((long long)cb * U + t) * H + j]) + r_s[cb * 9 + cj];
             const float tc = tanhf(c);
             const float dc = dh * go * (1.f - tc * tc) + dc_state;
-            __nv_bfloat16* d = dG + ((long long)t * B + cb) * G4 + j;
+            __nv_bfloat16* d = dG + ((long long)t * Bt + cb) * G4 + j;
             d[0] = __float2bfloat16_rn(dc * gg * gi * (1.f - gi));
             d[H] = __float2bfloat16_rn(dc * cp * gf * (1.f - gf));
             d[2 * H] = __float2bfloat16_rn(dc * gi * (1.f - gg * gg));
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
 using namespace pk;
 
 static int lstm_seq_check(int B, int U, int H) {
-    PK_CHECK_ARG(B >= 1 && B <= LS_MB, "persistent LSTM handles at most 32 sequences per launch");
+    PK_CHECK_ARG(B >= 1, "empty batch");
     PK_CHECK_ARG(U >= 1 && H % 64 == 0 && H / LS_HJ <= num_sms(), "H must be a multiple of 64 with H/8 <= #SMs");
     return 0;
 }
@@ -246,14 +248,23 @@ extern "C" int pk_lstm_seq_fwd(const float* gx, const void* w_hh_bf16, void* out
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
     __nv_bfloat16* hx = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(ws) + 256);
-    PK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
     const int smem = 2 * 32 * (H + LS_PAD) * 2 + 32 * 33 * 4;
     const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
-    void* args[] = {(void*)&gx, (void*)&w, (void*)&out, (void*)&hx, (void*)&gates_save, (void*)&cs, (void*)&B, (void*)&U, (void*)&H, (void*)&counter};
     const void* fn = out_dtype == PK_BF16 ? (const void*)lstm_seq_fwd_kernel<__nv_bfloat16> : (const void*)lstm_seq_fwd_kernel<float>;
     PK_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PK_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(H / LS_HJ), dim3(LS_THREADS), args, smem, st));
-    count_launch();
+    const size_t es = out_dtype == PK_BF16 ? 2 : 4;
+    for (int b0 = 0; b0 < B; b0 += LS_MB) {                    // sequences are independent: 32 per cooperative launch
+        int nb = B - b0 < LS_MB ? B - b0 : LS_MB, Bt = B;
+        const float* gx_c = gx + (long long)b0 * U * 4 * H;
+        void* out_c = reinterpret_cast<unsigned char*>(out) + (size_t)b0 * U * H * es;
+        float* gs_c = gates_save + (long long)b0 * 4 * H;
+        float* cs_c = cs + (long long)b0 * H;
+        PK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+        void* args[] = {(void*)&gx_c, (void*)&w, (void*)&out_c, (void*)&hx, (void*)&gs_c, (void*)&cs_c, (void*)&nb, (void*)&Bt, (void*)&U, (void*)&H,
+                        (void*)&counter};
+        PK_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(H / LS_HJ), dim3(LS_THREADS), args, smem, st));
+        count_launch();
+    }
     return 0;
 }
 extern "C" int pk_lstm_seq_bwd(const void* dout, int dtype, const float* gates_save, const float* cs, const void* w_hh_bf16, void* dG_bf16,
@@ -262,15 +273,22 @@ extern "C" int pk_lstm_seq_bwd(const void* dout, int dtype, const float* gates_s
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
-    PK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
     const int G4 = 4 * H;
     const int smem = LS_HJ * (G4 + LS_PAD) * 2 + 2 * 32 * (G4 / 4 + LS_PAD) * 2 + 32 * 9 * 4;
     const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
-    __nv_bfloat16* dg = reinterpret_cast<__nv_bfloat16*>(dG_bf16);
-    void* args[] = {(void*)&dout, (void*)&gates_save, (void*)&cs, (void*)&w, (void*)&dg, (void*)&B, (void*)&U, (void*)&H, (void*)&counter};
     const void* fn = dtype == PK_BF16 ? (const void*)lstm_seq_bwd_kernel<__nv_bfloat16> : (const void*)lstm_seq_bwd_kernel<float>;
     PK_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PK_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(H / LS_HJ), dim3(LS_THREADS), args, smem, st));
-    count_launch();
+    const size_t es = dtype == PK_BF16 ? 2 : 4;
+    for (int b0 = 0; b0 < B; b0 += LS_MB) {
+        int nb = B - b0 < LS_MB ? B - b0 : LS_MB, Bt = B;
+        const void* dout_c = reinterpret_cast<const unsigned char*>(dout) + (size_t)b0 * U * H * es;
+        const float* gs_c = gates_save + (long long)b0 * G4;
+        const float* cs_c = cs + (long long)b0 * H;
+        __nv_bfloat16* dg = reinterpret_cast<__nv_bfloat16*>(dG_bf16) + (long long)b0 * G4;
+        PK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+        void* args[] = {(void*)&dout_c, (void*)&gs_c, (void*)&cs_c, (void*)&w, (void*)&dg, (void*)&nb, (void*)&Bt, (void*)&U, (void*)&H, (void*)&counter};
+        PK_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(H / LS_HJ), dim3(LS_THREADS), args, smem, st));
+        count_launch();
+    }
     return 0;
 }

@@ -512,7 +512,7 @@ class LstmLayerFn(torch.autograd.Function):
         out = _new((B, U, H), like=x)
         gates = torch.empty(U, B, 4 * H, dtype=torch.float32, device=x.device)
         cs = torch.empty(U, B, H, dtype=torch.float32, device=x.device)
-        ctx.persistent = (x.dtype == torch.bfloat16 and B <= 32 and H % 64 == 0 and H // 8 <= 148)
+        ctx.persistent = (x.dtype == torch.bfloat16 and H % 64 == 0 and H // 8 <= 148)      # any batch: 32 sequences per cooperative launch
         if ctx.persistent:
             # whole recurrence in one cooperative launch (pika_b200/csrc/lstm_seq.cu)
             K.lstm_seq_fwd(gx, whh_parts[0], out, gates, cs)

@@ -85,6 +85,7 @@ class Frontend:
         self.window, self.twiddle, self.mel_w, self.mel_lo, self.mel_hi = t(win), t(tw), t(w.astype(np.float32)), t(lo), t(hi_i)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self._ws = None
+        self.dither_seed = 0x243F6A88          # advanced once per batch: every batch draws fresh dither noise
 
     @staticmethod
     def lengths(n_samples, rate):
@@ -109,15 +110,21 @@ class Frontend:
                                   P(n_frames), B, n_max, t_max, self.n_mel, self.lctx, self.rctx, P(self.window), P(self.twiddle),
                                   P(self.mel_w), P(self.mel_lo), P(self.mel_hi), ctypes.c_float(self.opts.preemphasis_coefficient),
                                   int(cmn), P(offset), P(scale), int(f0), int(fs), int(t0), int(ts), P(out), K._dt(out), P(wave),
-                                  P(self._ws), ctypes.c_longlong(need), P(self.err), K._stream()), "pk_frontend_fwd")
+                                  P(self._ws), ctypes.c_longlong(need), P(self.err), ctypes.c_float(self.opts.dither),
+                                  ctypes.c_uint32(self._next_dither_seed()), K._stream()), "pk_frontend_fwd")
         return (out, wave) if want_wave else out
 
-    def fbank(self, wave_f32, n_frames, t_max):
+    def _next_dither_seed(self):
+        self.dither_seed = (self.dither_seed * 1664525 + 1013904223) & 0xFFFFFFFF
+        return self.dither_seed
+
+    def fbank(self, wave_f32, n_frames, t_max, dither=None, seed=None):
         """wave f32 [B, n] of int16-scaled samples -> [B, t_max, n_mel] log-mel (rows >= n_frames[b] undefined)."""
         B = wave_f32.shape[0]
         feats = torch.zeros(B, t_max, self.n_mel, dtype=torch.float32, device=self.device)
         P = K._P
         check(lib.pk_fbank(P(wave_f32), ctypes.c_longlong(wave_f32.stride(0)), P(n_frames), B, t_max, self.n_mel, P(self.window),
                            P(self.twiddle), P(self.mel_w), P(self.mel_lo), P(self.mel_hi),
-                           ctypes.c_float(self.opts.preemphasis_coefficient), P(feats), K._stream()), "pk_fbank")
+                           ctypes.c_float(self.opts.preemphasis_coefficient), P(feats), ctypes.c_float(self.opts.dither if dither is None else dither),
+                           ctypes.c_uint32(self._next_dither_seed() if seed is None else seed), K._stream()), "pk_fbank")
         return feats

@@ -129,7 +129,8 @@ def _frontend_for(args, device):
     key = (args.feat_config, args.lctx, args.rctx, str(device))
     if key not in _frontends:
         opts = FbankOptions.from_config(args.feat_config) if args.feat_config else FbankOptions(num_mel_bins=args.feats_dim)
-        opts.dither = 0.0 if getattr(args, "no_dither", True) else opts.dither
+        if getattr(args, "no_dither", False):          # explicit opt-out (parity runs); otherwise the feature config decides
+            opts.dither = 0.0
         _frontends[key] = Frontend(opts, args.lctx, args.rctx, device)
     return _frontends[key]
 

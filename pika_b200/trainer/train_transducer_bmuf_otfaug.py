@@ -165,7 +165,8 @@ def main(argv=None):
     log_f.write('*' * 60 + '\n')
     log_f.flush()
     opts = FbankOptions.from_config(args.feat_config) if args.feat_config else FbankOptions(num_mel_bins=args.feats_dim)
-    opts.dither = 0.0        # Kaldi's RNG dither is not reproduced; features are deterministic
+    # opts.dither is honoured (egs/fbank.conf: dither=1): counter-based Gaussian dither in the fbank kernel; set dither=0 in the
+    # feature config for bit-reproducible features (Kaldi's own RNG stream is not reproduced)
     args.frontend = Frontend(opts, args.lctx, args.rctx, dev)
     args.offset = args.scale = None
     if args.cmvn_stats:

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pika_b200 import engine as E
 E.set_precision("bf16")
-B, T, heads = 32, int(os.environ.get("T", 994)), 16
+B, T, heads = int(os.environ.get("B", 32)), int(os.environ.get("T", 994)), 16
 D = heads * 64
 g = torch.Generator(device="cuda").manual_seed(1)
 qkv0 = (torch.randn(B, T, 3 * D, generator=g, device="cuda") * 0.5).bfloat16()

@@ -195,6 +195,75 @@ def golden_decode_big():
                         dims=np.array([V, B, Tp, beam, nbest]), **cases)
 
 
+class _FakeFst:
+    """the slice of the kaldi.fstext VectorFst interface decoder/sorted_matcher.py uses, over an in-memory arc table"""
+
+    class _W:
+        def __init__(self, v):
+            self.value = v
+
+    class _Arc:
+        def __init__(self, il, w, ns):
+            self.ilabel, self.weight, self.nextstate = il, _FakeFst._W(w), ns
+
+    class _Iter:
+        def __init__(self, arcs):
+            self.arcs, self.pos = arcs, 0
+
+        def seek(self, i):
+            self.pos = i
+
+        def done(self):
+            return self.pos >= len(self.arcs)
+
+        def value(self):
+            return _FakeFst._Arc(*self.arcs[self.pos])
+
+    def __init__(self, arcs, finals):
+        self._arcs, self._finals = arcs, finals
+
+    def arcs(self, state):
+        return _FakeFst._Iter(self._arcs[state])
+
+    def final(self, state):
+        return _FakeFst._W(self._finals[state])
+
+
+def golden_decode_fst():
+    """Reference decode_batch with on-the-fly FST shallow fusion (lm_scorer = the reference's own SortedMatcher,
+    decoder/sorted_matcher.py, over a toy back-off LM held in an in-memory stand-in for the PyKaldi VectorFst): the V=40 model and
+    inputs of decode_small, beam 4 and 8, lm_scorer_scale 0.5, nonblk_reward 0.45."""
+    import types
+    ref_shim.load_beam_module()
+    from decoder.transducer_decoder import TransducerDecoder
+    from decoder.sorted_matcher import SortedMatcher
+    import decoder.beam_transducer as bt
+    from fixture_utils import decode_fixture_reinit
+    from make_inputs import toy_backoff_lm
+    V = 40
+    m = build_ref_model(V)
+    m.eval()
+    decode_fixture_reinit(m)
+    d = np.load(os.path.join(HERE, "decode_small.npz"))
+    x, tl = torch.from_numpy(d["x"]), torch.from_numpy(d["tlens"])
+    arcs, finals = toy_backoff_lm(V)
+    matcher = SortedMatcher(_FakeFst(arcs, finals), max(len(a) for a in arcs), V + 2, 1, [])
+    cases = {}
+    for name, beam, nbest in [("b4", 4, 2), ("b8", 8, 4)]:
+        dargs = types.SimpleNamespace(las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None, nonblk_reward=0.45)
+        dec = TransducerDecoder(m, 3, beam, n_best=nbest, blk=0, global_scorer=bt.GlobalScorer(), sm_scale=1.0, cuda=False,
+                                lm_scorer=matcher, lm_scorer_scale=0.5, beam_prune=True, args=dargs)
+        with torch.no_grad():
+            ret, _ = dec.decode_batch(x, tl, max_len=[int(t) + 100 for t in tl])
+        for b in range(3):
+            for n in range(nbest):
+                cases["%s_pred_%d_%d" % (name, b, n)] = np.array([int(t) for t in ret["predictions"][b][n]], np.int64)
+                cases["%s_score_%d_%d" % (name, b, n)] = np.array(float(ret["scores"][b][n]))
+        print("decode_fst", name, [[int(t) for t in cases["%s_pred_%d_0" % (name, b)] if t != 0] for b in range(3)],
+              [round(float(cases["%s_score_%d_0" % (name, b)]), 3) for b in range(3)])
+    np.savez_compressed(os.path.join(HERE, "decode_fst.npz"), **cases)
+
+
 def golden_encoder_eval():
     """BASELINE config 1: encoder forward, 1 utterance, T=200, eval mode."""
     m = build_ref_model(40)
@@ -452,6 +521,6 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["rnnt", "frontend", "specaug", "encoder", "model", "decode", "mbr", "bmuf"]
     table = dict(rnnt=golden_rnnt, frontend=golden_frontend, specaug=golden_specaug,
                  encoder=golden_encoder_eval, model=golden_model, decode=golden_decode, mbr=golden_mbr, bmuf=golden_bmuf,
-                 model_full=golden_model_full, decode_big=golden_decode_big)
+                 model_full=golden_model_full, decode_big=golden_decode_big, decode_fst=golden_decode_fst)
     for w in which:
         table[w]()

@@ -143,3 +143,37 @@ def test_decode_bf16_token_agreement_with_reference(golden_dir):
     _record("decode_big_bf16", dict(same_label_seq=same_seq, utts=B, label_match=tok_match, labels=tok_total, score_rel_err=score_err))
     assert tok_match >= 0.8 * tok_total, (tok_match, tok_total)
     assert score_err < 0.15            # measured 0.06 (gpurun_out/parity_measured.jsonl): a flipped near-tie changes one label's log-prob
+
+
+@pytest.mark.parametrize("name,beam,nbest", [("b4", 4, 2), ("b8", 8, 4)])
+def test_decode_fst_shallow_fusion_matches_reference(golden_dir, name, beam, nbest):
+    """on-the-fly FST shallow fusion inside the device beam step (pk_beam_advance_lm) against the reference's own SortedMatcher +
+    BeamMergeTransducer run over the same toy back-off LM (tests/golden/decode_fst.npz, make_golden.py:golden_decode_fst):
+    lm_scorer_scale 0.5, nonblk_reward 0.45; bit-exact tokens, scores 1e-3."""
+    from make_inputs import toy_backoff_lm
+    from pika_b200 import engine
+    from pika_b200.decoder.beam_transducer import GlobalScorer
+    from pika_b200.decoder.sorted_matcher import SortedMatcher
+    from pika_b200.decoder.transducer_decoder import TransducerDecoder
+    d = np.load(os.path.join(golden_dir, "decode_small.npz"))
+    f = np.load(os.path.join(golden_dir, "decode_fst.npz"))
+    arcs, finals = toy_backoff_lm(40)
+    matcher = SortedMatcher((arcs, finals), max(len(a) for a in arcs), 42, 1, [])
+    engine.set_precision("fp32")
+    try:
+        m = build()
+        dargs = types.SimpleNamespace(las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None, nonblk_reward=0.45)
+        dec = TransducerDecoder(m, 3, beam, n_best=nbest, blk=0, global_scorer=GlobalScorer(), sm_scale=1.0, cuda=True, beam_prune=True,
+                                lm_scorer=matcher, lm_scorer_scale=0.5, args=dargs)
+        x = torch.from_numpy(d["x"]).cuda()
+        tl = torch.from_numpy(d["tlens"])
+        ret, _ = dec.decode_batch(x, tl, max_len=[int(t) + 100 for t in tl])
+        for b in range(3):
+            for n in range(nbest):
+                hyp = [int(t.item()) for t in ret["predictions"][b][n]]
+                ref = f["%s_pred_%d_%d" % (name, b, n)].tolist()
+                assert hyp == ref, (name, b, n, hyp[:40], ref[:40])
+                sc = float(ret["scores"][b][n])
+                assert abs(sc - float(f["%s_score_%d_%d" % (name, b, n)])) < 1e-3 * abs(sc) + 1e-3
+    finally:
+        engine.set_precision("bf16")

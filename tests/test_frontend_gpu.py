@@ -102,6 +102,7 @@ def test_loader_feature_mode_matches_oracle(tmp_path):
     cfg = tmp_path / "fbank.conf"
     cfg.write_text("--window-type=hamming\n--sample-frequency=16000\n--dither=1\n--low-freq=40\n--high-freq=-200\n--num-mel-bins=80\n")
     a = loader_args(raw_batches=False, batch_first=True, feat_config=str(cfg))
+    a.no_dither = True              # the recipe config asks for dither = 1; parity against the (deterministic) oracle chain opts out
     random.seed(3); np.random.seed(3)
     (data, target, lens, ali_lens), = list(L.dataloader(lst, [], [], a))
     assert data.dtype == torch.float32 and not data.is_cuda and tuple(data.shape) == (4, int(lens.max()), 240)
@@ -114,3 +115,36 @@ def test_loader_feature_mode_matches_oracle(tmp_path):
         assert int(lens[i]) == ref.shape[0]
         np.testing.assert_allclose(data[i, :ref.shape[0]].numpy(), ref, atol=1e-2)
         assert np.abs(data[i, :ref.shape[0]].numpy() - ref).mean() < 5e-4
+
+
+def test_dither_is_gaussian_counter_based_and_off_by_default_in_parity_runs():
+    """FbankOptions.dither (egs/fbank.conf: dither=1): dither * N(0,1) per sample of every window.  Checked on silence, where the
+    features are the dither alone: the log-mel energies must match white noise of variance dither^2 through the same window / mel
+    filters; same seed -> identical features, new seed -> new noise, dither = 0 -> exactly the undithered features."""
+    from pika_b200.frontend import FbankOptions, Frontend
+    dev = torch.device("cuda", 0)
+    fe = Frontend(FbankOptions(num_mel_bins=80, low_freq=40.0, high_freq=-200.0, dither=1.0, window_type="hamming"), 1, 1, dev)
+    B, T = 2, 300
+    n = 400 + (T - 1) * 160
+    nf = torch.full((B,), T, dtype=torch.int32, device=dev)
+    silence = torch.zeros(B, n, device=dev)
+    f1 = fe.fbank(silence, nf, T, dither=2.0, seed=123)
+    f2 = fe.fbank(silence, nf, T, dither=2.0, seed=123)
+    f3 = fe.fbank(silence, nf, T, dither=2.0, seed=124)
+    assert torch.equal(f1, f2) and not torch.equal(f1, f3)
+    # expected mel energy of white noise of variance sigma^2 = 4: every FFT bin k carries sigma^2 * sum(window^2) * |1 - c e^{-jw_k}|^2
+    # (pre-emphasis x[i] - c x[i-1] shapes the flat spectrum; DC removal only touches bin 0), summed through the mel weights
+    win = fe.window.double().cpu().numpy()
+    c = fe.opts.preemphasis_coefficient
+    mel = fe.mel_w.double().cpu().numpy()
+    wk = 2.0 * np.pi * np.arange(mel.shape[1]) / 512.0
+    gain = 1.0 + c * c - 2.0 * c * np.cos(wk)
+    expect = np.log(4.0 * (win ** 2).sum() * (mel * gain[None, :]).sum(1))
+    got = f1.double().cpu().numpy().mean((0, 1))
+    # E[log X] of a weighted chi-square sum sits a little below log E[X] (more for the narrow low-frequency filters): 0.35 in log energy
+    assert np.abs(got - expect).max() < 0.35, (got[:8], expect[:8])
+    loud = (torch.randn(B, n, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 3000).round()
+    g0 = fe.fbank(loud, nf, T, dither=0.0, seed=1)
+    g1 = fe.fbank(loud, nf, T, dither=1.0, seed=1)
+    diff = (g1 - g0).abs().max().item()
+    assert 0.0 < diff < 0.05                         # 1 LSB-class noise against a 3000-amplitude signal moves log energies by < 5e-2
