@@ -45,7 +45,8 @@ constexpr int TA_OFF_STAT = 0;                    // two stationary tiles
 constexpr int TA_OFF_RING = 2 * TA_TILE_S;        // NST x (X1, X2)
 constexpr int TA_OFF_ABUF = TA_OFF_RING + TA_NST * 2 * TA_TILE_X;      // [2 groups][2] A tiles of 16 KB
 constexpr int TA_OFF_VEC = TA_OFF_ABUF + 4 * TA_TILE_S;                // [NST][2][64] floats
-constexpr int TA_OFF_BAR = TA_OFF_VEC + TA_NST * 2 * TA_BC * 4;
+constexpr int TA_OFF_SALT = TA_OFF_VEC + TA_NST * 2 * TA_BC * 4;         // [2 groups][2][64] dropout row salts of the streamed queries (MODE 2)
+constexpr int TA_OFF_BAR = TA_OFF_SALT + 2 * 2 * TA_BC * 4;
 constexpr int TA_SMEM = TA_OFF_BAR + 256 + 1024;
 constexpr int TA_SCR_LD = 68;                     // floats per row of the merge scratch (aliases the ring)
 static_assert(TA_BR * TA_SCR_LD * 4 <= TA_NST * 2 * TA_TILE_X, "merge scratch must fit in the ring");
@@ -102,92 +103,90 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================================================== TMA loader
-        if (lane == 0) {
-            const CUtensorMap* ma0 = (MODE == 2) ? &p.k : &p.q;
-            const CUtensorMap* ma1 = (MODE == 2) ? &p.v : &p.dout;
-            const CUtensorMap* mx1 = (MODE == 2) ? &p.q : &p.k;
-            const CUtensorMap* mx2 = (MODE == 2) ? &p.dout : &p.v;
-            mbar_arrive_expect_tx(stat_full, (MODE == 0 ? 1 : 2) * TA_TILE_S);
-            for (int half = 0; half < 2; ++half) {
-                tma_load_3d(smem + TA_OFF_STAT + half * TA_TILE_X, ma0, stat_full, h * 64, row_base + half * 64, b);
-                if (MODE != 0) tma_load_3d(smem + TA_OFF_STAT + TA_TILE_S + half * TA_TILE_X, ma1, stat_full, h * 64, row_base + half * 64, b);
+        // ===================================================== TMA loader (converged warp, one elected lane issues)
+        const uint32_t lead = elect_one_u32();
+        const CUtensorMap* ma0 = (MODE == 2) ? &p.k : &p.q;
+        const CUtensorMap* ma1 = (MODE == 2) ? &p.v : &p.dout;
+        const CUtensorMap* mx1 = (MODE == 2) ? &p.q : &p.k;
+        const CUtensorMap* mx2 = (MODE == 2) ? &p.dout : &p.v;
+        mbar_arrive_expect_tx_p(stat_full, (MODE == 0 ? 1 : 2) * TA_TILE_S, lead);
+        for (int half = 0; half < 2; ++half) {
+            tma_load_3d_p(smem + TA_OFF_STAT + half * TA_TILE_X, ma0, stat_full, h * 64, row_base + half * 64, b, lead);
+            if (MODE != 0) tma_load_3d_p(smem + TA_OFF_STAT + TA_TILE_S + half * TA_TILE_X, ma1, stat_full, h * 64, row_base + half * 64, b, lead);
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* x1 = smem + TA_OFF_RING + stage * 2 * TA_TILE_X;
+            mbar_arrive_expect_tx_p(&full_bar[stage], 2 * TA_TILE_X + (MODE == 2 ? 2 * TA_BC * 4 : 0), lead);
+            tma_load_3d_p(x1, mx1, &full_bar[stage], h * 64, j * TA_BC, b, lead);
+            tma_load_3d_p(x1 + TA_TILE_X, mx2, &full_bar[stage], h * 64, j * TA_BC, b, lead);
+            if (MODE == 2) {
+                const size_t off = (size_t)bh * p.Tpad + (size_t)j * TA_BC;
+                bulk_load_p(vec + (stage * 2 + 0) * TA_BC, p.lse + off, TA_BC * 4, &full_bar[stage], lead);
+                bulk_load_p(vec + (stage * 2 + 1) * TA_BC, p.dsum + off, TA_BC * 4, &full_bar[stage], lead);
             }
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_tiles; ++j) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* x1 = smem + TA_OFF_RING + stage * 2 * TA_TILE_X;
-                mbar_arrive_expect_tx(&full_bar[stage], 2 * TA_TILE_X + (MODE == 2 ? 2 * TA_BC * 4 : 0));
-                tma_load_3d(x1, mx1, &full_bar[stage], h * 64, j * TA_BC, b);
-                tma_load_3d(x1 + TA_TILE_X, mx2, &full_bar[stage], h * 64, j * TA_BC, b);
-                if (MODE == 2) {
-                    const size_t off = (size_t)bh * p.Tpad + (size_t)j * TA_BC;
-                    bulk_load(vec + (stage * 2 + 0) * TA_BC, p.lse + off, TA_BC * 4, &full_bar[stage]);
-                    bulk_load(vec + (stage * 2 + 1) * TA_BC, p.dsum + off, TA_BC * 4, &full_bar[stage]);
-                }
-                if (++stage == TA_NST) { stage = 0; phase ^= 1; }
-            }
+            if (++stage == TA_NST) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = make_idesc_bf16(TA_BR, TA_BC, false, false);   // A K-major, B K-major (both over d)
-            constexpr uint32_t idesc2 = make_idesc_bf16(TA_BR, 64, false, true);       // A K-major (over the streamed index), B MN-major
-            const uint32_t sbase = smem_u32(smem);
-            const uint64_t kdesc = make_smem_desc_sw128(0, 16, 1024);                  // K-major tile: rows of 128 B
-            const uint64_t mdesc = make_smem_desc_sw128(0, 8192, 1024);                // MN-major tile: 8-row atoms along K
-            auto kmaj = [&](uint32_t addr, int k4) { return kdesc + (((addr + k4 * 32) >> 4) & 0x3FFF); };
-            auto mnmaj = [&](uint32_t addr, int k4) { return mdesc + (((addr + k4 * 2048) >> 4) & 0x3FFF); };
-            mbar_wait(stat_full, 0);
+        // ===================================================== MMA issuer (converged warp, one elected lane issues)
+        const uint32_t lead = elect_one_u32();
+        constexpr uint32_t idesc1 = make_idesc_bf16(TA_BR, TA_BC, false, false);   // A K-major, B K-major (both over d)
+        constexpr uint32_t idesc2 = make_idesc_bf16(TA_BR, 64, false, true);       // A K-major (over the streamed index), B MN-major
+        const uint32_t sbase = smem_u32(smem);
+        const uint64_t kdesc = make_smem_desc_sw128(0, 16, 1024);                  // K-major tile: rows of 128 B
+        const uint64_t mdesc = make_smem_desc_sw128(0, 8192, 1024);                // MN-major tile: 8-row atoms along K
+        // descriptor of a tile = template + (address >> 4); a k16 step adds a compile-time constant to the 14-bit address field (tiles are
+        // 1024-byte aligned and the whole buffer lies below 256 KB, so the field never carries): one 64-bit add per operand per MMA
+        auto kmaj = [&](uint32_t addr, int k4) { return kdesc + (uint64_t)((addr >> 4) & 0x3FFF) + (uint64_t)(k4 * 2); };
+        auto mnmaj = [&](uint32_t addr, int k4) { return mdesc + (uint64_t)((addr >> 4) & 0x3FFF) + (uint64_t)(k4 * 128); };
+        mbar_wait(stat_full, 0);
+        tc_fence_after();
+        const uint32_t st0 = sbase + TA_OFF_STAT, st1 = st0 + TA_TILE_S;
+        auto stage2 = [&](int t) {
+            const int g = t & 1, s = t % TA_NST;
+            mbar_wait(&a_ready[g], (t >> 1) & 1);
             tc_fence_after();
-            const uint32_t st0 = sbase + TA_OFF_STAT, st1 = st0 + TA_TILE_S;
-            auto stage2 = [&](int t) {
-                const int g = t & 1, s = t % TA_NST;
-                mbar_wait(&a_ready[g], (t >> 1) & 1);
-                tc_fence_after();
-                const uint32_t x1 = sbase + TA_OFF_RING + s * 2 * TA_TILE_X, x2 = x1 + TA_TILE_X;
-                const uint32_t a0 = sbase + TA_OFF_ABUF + (g * 2) * TA_TILE_S, a1 = a0 + TA_TILE_S;
+            const uint32_t x1 = sbase + TA_OFF_RING + s * 2 * TA_TILE_X, x2 = x1 + TA_TILE_X;
+            const uint32_t a0 = sbase + TA_OFF_ABUF + (g * 2) * TA_TILE_S, a1 = a0 + TA_TILE_S;
 #pragma unroll
-                for (int k4 = 0; k4 < TA_BC / 16; ++k4) {
-                    if (MODE == 0) umma_bf16(tmem_base + TA_COL_ACC + g * 64, kmaj(a0, k4), mnmaj(x2, k4), idesc2, k4 > 0 ? 1u : 0u);
-                    if (MODE == 1) umma_bf16(tmem_base + TA_COL_ACC, kmaj(a0, k4), mnmaj(x1, k4), idesc2, (t > 0 || k4 > 0) ? 1u : 0u);
-                    if (MODE == 2) {
-                        umma_bf16(tmem_base + TA_COL_ACC + 64, kmaj(a0, k4), mnmaj(x2, k4), idesc2, (t > 0 || k4 > 0) ? 1u : 0u);   // dV += Pd^T dO
-                        umma_bf16(tmem_base + TA_COL_ACC, kmaj(a1, k4), mnmaj(x1, k4), idesc2, (t > 0 || k4 > 0) ? 1u : 0u);        // dK += dS^T Q
-                    }
+            for (int k4 = 0; k4 < TA_BC / 16; ++k4) {
+                if (MODE == 0) umma_bf16_p(tmem_base + TA_COL_ACC + g * 64, kmaj(a0, k4), mnmaj(x2, k4), idesc2, k4 > 0 ? 1u : 0u, lead);
+                if (MODE == 1) umma_bf16_p(tmem_base + TA_COL_ACC, kmaj(a0, k4), mnmaj(x1, k4), idesc2, (t > 0 || k4 > 0) ? 1u : 0u, lead);
+                if (MODE == 2) {
+                    umma_bf16_p(tmem_base + TA_COL_ACC + 64, kmaj(a0, k4), mnmaj(x2, k4), idesc2, (t > 0 || k4 > 0) ? 1u : 0u, lead);   // dV += Pd^T dO
+                    umma_bf16_p(tmem_base + TA_COL_ACC, kmaj(a1, k4), mnmaj(x1, k4), idesc2, (t > 0 || k4 > 0) ? 1u : 0u, lead);        // dK += dS^T Q
                 }
-                umma_commit(&pv_done[g]);
-                umma_commit(&empty_bar[s]);
-            };
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_tiles; ++j) {
-                const int g = j & 1;
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t x1 = sbase + TA_OFF_RING + stage * 2 * TA_TILE_X, x2 = x1 + TA_TILE_X;
-                // S (and dP) of group g may be overwritten as soon as the group has pulled tile j-2 into registers (s_free), long before it
-                // finishes the exponentials of that tile: the next stage-1 product is then ready the moment the group comes back for it
-                // (ncu of the first version: 30-50 % of all stall samples sat on the s_ready wait, profiles/r02_attention_tc.txt)
-                if (j >= 2) { mbar_wait(&s_free[g], ((j >> 1) - 1) & 1); tc_fence_after(); }
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem_base + TA_COL_S + g * 64, kmaj(st0, k4), kmaj(x1, k4), idesc1, k4 > 0 ? 1u : 0u);
-                if (MODE != 0) {
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem_base + TA_COL_DP + g * 64, kmaj(st1, k4), kmaj(x2, k4), idesc1, k4 > 0 ? 1u : 0u);
-                }
-                umma_commit(&s_ready[g]);
-                // second stage of tile j-2, i.e. AFTER the stage-1 products of the next tile of the same group have been queued: the
-                // issue order S0 S1 S2 P0 S3 P1 ... keeps a finished S waiting for each group when it comes back from its exponentials
-                // (with S(j+1) behind P(j-1) the thread sat in the a_ready wait and the groups idled, profiles/r02_attention_tc_v1.ncu.txt)
-                if (j >= 2) stage2(j - 2);
-                if (++stage == TA_NST) { stage = 0; phase ^= 1; }
             }
-            if (n_tiles >= 2) stage2(n_tiles - 2);
-            stage2(n_tiles - 1);
-            umma_commit(final_bar);
+            umma_commit_p(&pv_done[g], lead);
+            umma_commit_p(&empty_bar[s], lead);
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int g = j & 1;
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t x1 = sbase + TA_OFF_RING + stage * 2 * TA_TILE_X, x2 = x1 + TA_TILE_X;
+            // S (and dP) of group g may be overwritten as soon as the group has pulled tile j-2 into registers (s_free), long before it
+            // finishes the exponentials of that tile
+            if (j >= 2) { mbar_wait(&s_free[g], ((j >> 1) - 1) & 1); tc_fence_after(); }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) umma_bf16_p(tmem_base + TA_COL_S + g * 64, kmaj(st0, k4), kmaj(x1, k4), idesc1, k4 > 0 ? 1u : 0u, lead);
+            if (MODE != 0) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) umma_bf16_p(tmem_base + TA_COL_DP + g * 64, kmaj(st1, k4), kmaj(x2, k4), idesc1, k4 > 0 ? 1u : 0u, lead);
+            }
+            umma_commit_p(&s_ready[g], lead);
+            // second stage of tile j-2, i.e. AFTER the stage-1 products of the next tile of the same group have been queued: the
+            // issue order S0 S1 S2 P0 S3 P1 ... keeps a finished S waiting for each group when it comes back from its exponentials
+            if (j >= 2) stage2(j - 2);
+            if (++stage == TA_NST) { stage = 0; phase ^= 1; }
         }
+        if (n_tiles >= 2) stage2(n_tiles - 2);
+        stage2(n_tiles - 1);
+        umma_commit_p(final_bar, lead);
     } else {
         // ===================================================== element-wise groups
         const int g = (warp - 2) >> 2;
@@ -201,6 +200,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
         uint8_t* a1 = a0 + TA_TILE_S;
         const int sw = r & 7;
         const bool use_drop = p.thresh16 != 0u;
+        const uint32_t row_salt = drop_row_salt(stat_row0 + (uint64_t)srow, p.seed);     // MODE 0/1: the probability row is this thread's row
 
         float o_acc[64];                                       // MODE 0: running O of this group's tiles (scale = m_run)
         float m_run = -INFINITY, l_run = 0.f;
@@ -241,9 +241,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&s_free[g]);
+                if (nvalid < TA_BC) {                          // last tile only (uniform): keys beyond the sequence score -inf -> probability 0
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) if (c >= nvalid) sr[c] = 0xff800000u;
+                }
                 float mx = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 64; ++c) mx = fmaxf(mx, c < nvalid ? __uint_as_float(sr[c]) : -INFINITY);
+                for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
                 const float m_new = fmaxf(m_run, mx * c2);     // finite: every tile holds a valid column
                 const float corr = ex2_approx(m_run - m_new);  // 0 on the group's first tile
 #pragma unroll
@@ -255,13 +259,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int c = ch * 8 + e;
-                        pr[e] = c < nvalid ? ex2_approx(fmaf(__uint_as_float(sr[c]), c2, -m_new)) : 0.f;
+                        pr[e] = ex2_approx(fmaf(__uint_as_float(sr[c]), c2, -m_new));
                         sum += pr[e];
                     }
                     if (use_drop) {
 #pragma unroll
                         for (int e2 = 0; e2 < 4; ++e2) {
-                            const uint32_t km = drop_pair(stat_row0 + (uint64_t)srow, (uint32_t)p.Tp2, (uint32_t)((col0 + ch * 8) >> 1) + e2, p.seed, p.thresh16);
+                            const uint32_t km = drop_pair(row_salt, (uint32_t)((col0 + ch * 8) >> 1) + e2, p.thresh16);
                             if (!(km & 1u)) pr[2 * e2] = 0.f;
                             if (!(km & 2u)) pr[2 * e2 + 1] = 0.f;
                         }
@@ -275,6 +279,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
                 if (it > 0) mbar_wait(&pv_done[g], (it - 1) & 1);       // the A tiles of this group are free again
                 const float* lse_t = vec + ((j % TA_NST) * 2 + 0) * TA_BC;
                 const float* dsum_t = lse_t + TA_BC;
+                uint32_t* qsalt_t = reinterpret_cast<uint32_t*>(smem + TA_OFF_SALT) + (g * 2 + (it & 1)) * TA_BC;
+                if (MODE == 2 && use_drop) {
+                    // the probability rows of this tile are the streamed queries: one salt per query, shared by the group (double
+                    // buffered by tile parity, so a group barrier per tile is all the ordering it needs)
+                    if (r < TA_BC) qsalt_t[r] = drop_row_salt(stat_row0 + (uint64_t)(col0 + r), p.seed);
+                    named_bar_sync(2 + g, 128);
+                }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t sr[32], dr[32];
@@ -282,6 +293,10 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
                     tmem_ld_32x32(tq + TA_COL_DP + g * 64 + half * 32, dr);
                     tmem_ld_wait();
                     if (half == 1) { tc_fence_before(); mbar_arrive(&s_free[g]); }       // S / dP of this tile are in registers
+                    if (nvalid < TA_BC) {                      // last tile only (uniform): streamed indices beyond the sequence get probability 0
+#pragma unroll                                                 // (their dP is 0 and the lse / D pads are zero-initialised, so dS = 0 * finite)
+                        for (int c = 0; c < 32; ++c) if (half * 32 + c >= nvalid) sr[c] = 0xff800000u;
+                    }
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch) {
                         float ds[8], pd[8];
@@ -290,8 +305,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
                             if (MODE == 1) {
 #pragma unroll
                                 for (int e2 = 0; e2 < 4; ++e2) {
-                                    const uint32_t km = drop_pair(stat_row0 + (uint64_t)srow, (uint32_t)p.Tp2,
-                                                                  (uint32_t)((col0 + half * 32 + ch * 8) >> 1) + e2, p.seed, p.thresh16);
+                                    const uint32_t km = drop_pair(row_salt, (uint32_t)((col0 + half * 32 + ch * 8) >> 1) + e2, p.thresh16);
                                     if (!(km & 1u)) keep &= ~(1u << (2 * e2));
                                     if (!(km & 2u)) keep &= ~(2u << (2 * e2));
                                 }
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
                                 for (int e2 = 0; e2 < 4; ++e2) {
                                     const int c_mine = half * 32 + ch * 8 + 2 * e2 + (lane & 1), c_other = c_mine ^ 1;
-                                    const uint32_t km = drop_pair(stat_row0 + (uint64_t)(col0 + c_mine), (uint32_t)p.Tp2, (uint32_t)(srow >> 1), p.seed, p.thresh16);
+                                    const uint32_t km = drop_pair(qsalt_t[c_mine], (uint32_t)(srow >> 1), p.thresh16);
                                     const uint32_t ko = __shfl_xor_sync(0xffffffffu, km, 1);
                                     const uint32_t bit = (lane & 1) ? 2u : 1u;
                                     const int e_mine = c_mine & 7, e_other = c_other & 7;
@@ -313,14 +327,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const int cl = half * 32 + ch * 8 + e;             // streamed index inside the tile
-                            const bool valid = cl < nvalid;
                             const float l2 = (MODE == 1) ? lse2 : lse_t[cl] * TA_LOG2E;
                             const float dd = (MODE == 1) ? dsum_r : dsum_t[cl];
                             const float pr = ex2_approx(fmaf(__uint_as_float(sr[ch * 8 + e]), c2, -l2));
                             const bool kp = (keep >> e) & 1u;
                             const float dpe = kp ? __uint_as_float(dr[ch * 8 + e]) * p.drop_scale : 0.f;
-                            ds[e] = valid ? pr * (dpe - dd) : 0.f;
-                            if (MODE == 2) pd[e] = (valid && kp) ? pr * p.drop_scale : 0.f;
+                            ds[e] = pr * (dpe - dd);
+                            if (MODE == 2) pd[e] = kp ? pr * p.drop_scale : 0.f;
                         }
                         const int chunk = half * 4 + ch;
                         if (MODE == 1) {

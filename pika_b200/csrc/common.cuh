@@ -68,13 +68,16 @@ PK_DEVICE uint32_t hash_u32(uint64_t idx, uint32_t seed) {
 // keep iff hash >= thresh where thresh = p * 2^32
 PK_DEVICE bool drop_keep(uint64_t idx, uint32_t seed, uint32_t thresh) { return hash_u32(idx, seed) >= thresh; }
 
-// Attention-probability dropout: one hash per PAIR of adjacent keys of a probability row, 16 bits per element (halves the
-// integer work of the mask, which is the largest ALU item of the fused attention kernels).  `grow` = row of the
-// [B*heads*T, T] probability matrix, kp = key >> 1, Tp2 = ceil(T / 2); returns keep bits (bit 0: even key, bit 1: odd key).
-// keep iff the 16-bit lane >= thresh16 = round(p * 65536); the keep-scale is 1 / (1 - thresh16 / 65536).
-PK_DEVICE uint32_t drop_pair(uint64_t grow, uint32_t Tp2, uint32_t kp, uint32_t seed, uint32_t thresh16) {
-    const uint32_t h = hash_u32(grow * (uint64_t)Tp2 + kp, seed);
-    return ((h & 0xFFFFu) >= thresh16 ? 1u : 0u) | ((h >> 16) >= thresh16 ? 2u : 0u);
+// Attention-probability dropout: one hash per PAIR of adjacent keys of a probability row, 16 bits per element.  The mask is the
+// largest integer-ALU item of the fused attention kernels, so the per-pair part is kept to seven instructions: a per-row salt
+// (full-strength hash of the row index, computed once per row) plus a two-round multiply / xor-shift of (salt + pair index).
+// `salt` = drop_row_salt(row of the [B*heads*T, T] probability matrix, seed); kp = key >> 1; returns keep bits (bit 0: even key,
+// bit 1: odd key).  keep iff the 16-bit lane >= thresh16 = round(p * 65536); the keep-scale is 1 / (1 - thresh16 / 65536).
+PK_DEVICE uint32_t drop_row_salt(uint64_t grow, uint32_t seed) { return hash_u32(grow, seed); }
+PK_DEVICE uint32_t drop_pair(uint32_t salt, uint32_t kp, uint32_t thresh16) {
+    uint32_t x = (salt + kp) * 0x9E3779B1u;
+    x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
+    return ((x & 0xFFFFu) >= thresh16 ? 1u : 0u) | ((x >> 16) >= thresh16 ? 2u : 0u);
 }
 __host__ __device__ inline uint32_t drop_thresh16_of(float p) {
     if (p <= 0.f) return 0u;
@@ -329,6 +332,88 @@ PK_DEVICE void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                  "h"(mask)
                  : "memory");
+}
+
+// ---------------------------------------------------------------- predicated single-lane issue
+// The producer / MMA warps run their loops CONVERGED (all 32 lanes wait on the barriers and compute the same addresses) and only the
+// asynchronous instruction itself is predicated on one elected lane.  Inside an `if (lane == 0)` region the compiler has to wrap every
+// instruction that takes uniform-register operands (UTMALDG, UTCHMMA, UTCBAR) in an elect / R2UR / BRA.U.ANY loop -- ~15-20 SASS
+// instructions per tcgen05.mma, which made the single issuing thread the bottleneck of the attention kernels (12 small MMAs per tile,
+// profiles/r02_attention_tc_v4.ncu.txt).
+PK_DEVICE uint32_t elect_one_u32() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(pred));
+    return pred;
+}
+PK_DEVICE void mbar_arrive_expect_tx_p(uint64_t* bar, uint32_t bytes, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
+                 "r"(bytes), "r"(pred)
+                 : "memory");
+}
+PK_DEVICE void tma_load_3d_p(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+        "@q cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(pred)
+        : "memory");
+}
+PK_DEVICE void bulk_load_p(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "r"(pred)
+        : "memory");
+}
+PK_DEVICE void tma_load_4d_hint_p(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t pol, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %8, 0;\n\t"
+        "@q cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol), "r"(pred)
+        : "memory");
+}
+PK_DEVICE void tma_load_4d_2sm_hint_p(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t pol,
+                                      uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %8, 0;\n\t"
+        "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol), "r"(pred)
+        : "memory");
+}
+PK_DEVICE void umma_bf16_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
+        : "memory");
+}
+PK_DEVICE void umma_bf16_2sm_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
+        : "memory");
+}
+PK_DEVICE void umma_commit_p(uint64_t* bar, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(
+                     smem_u32(bar)),
+                 "r"(pred)
+                 : "memory");
+}
+PK_DEVICE void umma_commit_2sm_p(uint64_t* bar, uint16_t mask, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
+        "h"(mask), "r"(pred)
+        : "memory");
 }
 
 PK_DEVICE void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }

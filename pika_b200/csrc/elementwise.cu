@@ -425,9 +425,10 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
                     od[e] = o[e];
                 }
                 if (drop_thresh) {                                       // pair mask shared with the fused attention kernels (common.cuh)
+                    const uint32_t salt = drop_row_salt((uint64_t)r, seed);
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2) {
-                        const uint32_t km = drop_pair((uint64_t)r, (uint32_t)((n + 1) >> 1), (uint32_t)((c0 >> 1) + e2), seed, drop_thresh);
+                        const uint32_t km = drop_pair(salt, (uint32_t)((c0 >> 1) + e2), drop_thresh);
                         od[2 * e2] = (km & 1u) ? o[2 * e2] * drop_scale : 0.f;
                         od[2 * e2 + 1] = (km & 2u) ? o[2 * e2 + 1] * drop_scale : 0.f;
                     }
@@ -457,9 +458,10 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
                 V8<T>::load(P + r * ld_p + c0, pv[k]);
 #pragma unroll
                 if (drop_thresh) {
+                    const uint32_t salt = drop_row_salt((uint64_t)r, seed);
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2) {
-                        const uint32_t km = drop_pair((uint64_t)r, (uint32_t)((n + 1) >> 1), (uint32_t)((c0 >> 1) + e2), seed, drop_thresh);
+                        const uint32_t km = drop_pair(salt, (uint32_t)((c0 >> 1) + e2), drop_thresh);
                         d[k][2 * e2] = (km & 1u) ? d[k][2 * e2] * drop_scale : 0.f;
                         d[k][2 * e2 + 1] = (km & 2u) ? d[k][2 * e2 + 1] * drop_scale : 0.f;
                     }

@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(GemmCfg<BN, TWO>::THREADS, 1) gemm_tcgen05_ker
     const int k_iters_total = p.n_pairs * p.kz_count * p.num_k_blocks;
 
     if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
+        // ===================================================== TMA producer (converged warp; one elected lane issues, common.cuh)
+        {
+            const uint32_t lead = elect_one_u32();
             int stage = 0;
             uint32_t phase = 0;
             const int kzb = p.kz_count * p.num_k_blocks;
@@ -167,27 +168,27 @@ __global__ void __launch_bounds__(GemmCfg<BN, TWO>::THREADS, 1) gemm_tcgen05_ker
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
-                    if (!TWO || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (TWO ? 2 : 1) * Cfg::STAGE_BYTES);
+                    if (!TWO || rank == 0) mbar_arrive_expect_tx_p(&full_bar[stage], (TWO ? 2 : 1) * Cfg::STAGE_BYTES, lead);
                     const int k0 = kb * BK;
                     if (A_MN) {
 #pragma unroll
                         for (int c = 0; c < BM / 64; ++c) {
-                            if (TWO) tma_load_4d_2sm_hint(sa + c * (64 * BK * 2), ma, &full_bar[stage], m0 + c * 64, k0 + a_off, a2, a3, p.pol_a);
-                            else tma_load_4d_hint(sa + c * (64 * BK * 2), ma, &full_bar[stage], m0 + c * 64, k0 + a_off, a2, a3, p.pol_a);
+                            if (TWO) tma_load_4d_2sm_hint_p(sa + c * (64 * BK * 2), ma, &full_bar[stage], m0 + c * 64, k0 + a_off, a2, a3, p.pol_a, lead);
+                            else tma_load_4d_hint_p(sa + c * (64 * BK * 2), ma, &full_bar[stage], m0 + c * 64, k0 + a_off, a2, a3, p.pol_a, lead);
                         }
                     } else {
-                        if (TWO) tma_load_4d_2sm_hint(sa, ma, &full_bar[stage], k0, m0 + a_off, a2, a3, p.pol_a);
-                        else tma_load_4d_hint(sa, ma, &full_bar[stage], k0, m0 + a_off, a2, a3, p.pol_a);
+                        if (TWO) tma_load_4d_2sm_hint_p(sa, ma, &full_bar[stage], k0, m0 + a_off, a2, a3, p.pol_a, lead);
+                        else tma_load_4d_hint_p(sa, ma, &full_bar[stage], k0, m0 + a_off, a2, a3, p.pol_a, lead);
                     }
                     if (B_MN) {
 #pragma unroll
                         for (int c = 0; c < Cfg::B_ROWS / 64; ++c) {
-                            if (TWO) tma_load_4d_2sm_hint(sb + c * (64 * BK * 2), mbp, &full_bar[stage], n0 + c * 64, k0 + b_off, b2, b3, p.pol_b);
-                            else tma_load_4d_hint(sb + c * (64 * BK * 2), mbp, &full_bar[stage], n0 + c * 64, k0 + b_off, b2, b3, p.pol_b);
+                            if (TWO) tma_load_4d_2sm_hint_p(sb + c * (64 * BK * 2), mbp, &full_bar[stage], n0 + c * 64, k0 + b_off, b2, b3, p.pol_b, lead);
+                            else tma_load_4d_hint_p(sb + c * (64 * BK * 2), mbp, &full_bar[stage], n0 + c * 64, k0 + b_off, b2, b3, p.pol_b, lead);
                         }
                     } else {
-                        if (TWO) tma_load_4d_2sm_hint(sb, mbp, &full_bar[stage], k0, n0 + b_off, b2, b3, p.pol_b);
-                        else tma_load_4d_hint(sb, mbp, &full_bar[stage], k0, n0 + b_off, b2, b3, p.pol_b);
+                        if (TWO) tma_load_4d_2sm_hint_p(sb, mbp, &full_bar[stage], k0, n0 + b_off, b2, b3, p.pol_b, lead);
+                        else tma_load_4d_hint_p(sb, mbp, &full_bar[stage], k0, n0 + b_off, b2, b3, p.pol_b, lead);
                     }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                     if (++kb == p.num_k_blocks) {
@@ -203,8 +204,9 @@ __global__ void __launch_bounds__(GemmCfg<BN, TWO>::THREADS, 1) gemm_tcgen05_ker
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (the leader CTA's in TWO mode)
-        if (lane == 0 && rank == 0) {
+        // ===================================================== MMA issuer (the leader CTA's in TWO mode; converged warp, one lane issues)
+        if (rank == 0) {
+            const uint32_t lead = elect_one_u32();
             constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * BM : BM, BN, A_MN, B_MN);
             // K-major: 16 elements = 32 B inside the 128 B swizzle row; atoms of 8 rows (1024 B).
             // MN-major: 16 k-rows = two 8-row atoms (2048 B); 64-wide MN chunks 8192 B apart.
@@ -232,14 +234,14 @@ __global__ void __launch_bounds__(GemmCfg<BN, TWO>::THREADS, 1) gemm_tcgen05_ker
                     const uint64_t ad = a_desc0 + stage16, bd = b_desc0 + stage16;
 #pragma unroll
                     for (int k4 = 0; k4 < BK / 16; ++k4) {
-                        if (TWO) umma_bf16_2sm(d_tmem, ad + k4 * A_K16, bd + k4 * B_K16, idesc, (k > 0 || k4 > 0) ? 1u : 0u);
-                        else umma_bf16(d_tmem, ad + k4 * A_K16, bd + k4 * B_K16, idesc, (k > 0 || k4 > 0) ? 1u : 0u);
+                        if (TWO) umma_bf16_2sm_p(d_tmem, ad + k4 * A_K16, bd + k4 * B_K16, idesc, (k > 0 || k4 > 0) ? 1u : 0u, lead);
+                        else umma_bf16_p(d_tmem, ad + k4 * A_K16, bd + k4 * B_K16, idesc, (k > 0 || k4 > 0) ? 1u : 0u, lead);
                     }
-                    if (TWO) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+                    if (TWO) umma_commit_2sm_p(&empty_bar[stage], 3, lead); else umma_commit_p(&empty_bar[stage], lead);
                     stage16 += Cfg::STAGE_BYTES >> 4;
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; stage16 = 0; }
                 }
-                if (TWO) umma_commit_2sm(&tmem_full[acc], 3); else umma_commit(&tmem_full[acc]);
+                if (TWO) umma_commit_2sm_p(&tmem_full[acc], 3, lead); else umma_commit_p(&tmem_full[acc], lead);
             }
         }
     } else {
@@ -650,10 +652,11 @@ extern "C" int pk_gemm_bf16(const pk_gemm_desc* d, void* stream_v) {
     const bool plain_epi = d->bias == nullptr && d->act == PK_ACT_NONE && d->drop_p == 0.f && gp.aux_mode == PK_AUX_NONE;
     if (d->k_splits > 0) splits = d->k_splits;
     else if (gp.c_is_f32 && plain_epi && gp.zb0 == 1 && gp.zb1 == 1 && k_iters_total >= 16) {
-        // PK_GEMM_SPLIT_MODE: 0 = fill about two waves (round-1 default) | 1 = the split count (>= 8 k-blocks each, <= PK_GEMM_SPLIT_MAX)
-        // that wastes the least of the last wave, preferring fewer splits on ties
+        // PK_GEMM_SPLIT_MODE: 1 (default) = the split count (>= 8 k-blocks each, <= PK_GEMM_SPLIT_MAX = 16) that wastes the least of the last
+        // wave, preferring fewer splits on ties: fc2 wgrad 1138 -> 1269 TFLOP/s stand-alone, 71.0 -> 69.5 ms per step same box
+        // (profiles/r02_gemm_lab.txt) | 0 = fill about two waves (the round-1 rule)
         static int mode = -1, smax = -1;
-        if (mode < 0) { mode = env_int("PK_GEMM_SPLIT_MODE", 0); smax = env_int("PK_GEMM_SPLIT_MAX", 16); }
+        if (mode < 0) { mode = env_int("PK_GEMM_SPLIT_MODE", 1); smax = env_int("PK_GEMM_SPLIT_MAX", 16); }
         const int w = workers_max;
         if (mode == 0) {
             if (out_tiles < 2 * w) {

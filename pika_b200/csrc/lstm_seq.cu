@@ -92,6 +92,13 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float
     __syncthreads();
     for (int t = 0; t < U; ++t) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // this step's input-projection terms do not depend on h_{t-1}: fetch them now so that their L2 / HBM latency hides behind the
+        // all-gather and the product instead of sitting on the step's critical path
+        float gx_i = 0.f, gx_f = 0.f, gx_g = 0.f, gx_o = 0.f;
+        if (cb < B) {
+            const float* gxr = gx + ((long long)cb * U + t) * 4 * H + j0 + cj;
+            gx_i = __ldg(gxr); gx_f = __ldg(gxr + H); gx_g = __ldg(gxr + 2 * H); gx_o = __ldg(gxr + 3 * H);
+        }
         if (t > 0) {
             // all-gather of h_{t-1} (32 x H bf16) from L2 by the TMA engine: lane r of warp 0 copies row r
             const __nv_bfloat16* src = hx + (long long)((t - 1) & 1) * LS_MB * H;
@@ -121,11 +128,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float
         __syncthreads();
         // fused cell for (cb, j0 + cj); local gate rows: i = cj, f = 8 + cj, g = 16 + cj, o = 24 + cj
         if (cb < B) {
-            const float* gxr = gx + ((long long)cb * U + t) * 4 * H + j0 + cj;
-            const float gi = sigm(g_s[cb * 33 + cj] + gxr[0]);
-            const float gf = sigm(g_s[cb * 33 + 8 + cj] + gxr[H]);
-            const float gg = tanhf(g_s[cb * 33 + 16 + cj] + gxr[2 * H]);
-            const float go = sigm(g_s[cb * 33 + 24 + cj] + gxr[3 * H]);
+            const float gi = sigm(g_s[cb * 33 + cj] + gx_i);
+            const float gf = sigm(g_s[cb * 33 + 8 + cj] + gx_f);
+            const float gg = tanhf(g_s[cb * 33 + 16 + cj] + gx_g);
+            const float go = sigm(g_s[cb * 33 + 24 + cj] + gx_o);
             c_state = gf * c_state + gi * gg;
             const float hv = go * tanhf(c_state);
             out[((long long)cb * U + t) * H + j0 + cj] = from_f32<T>(hv);
@@ -172,6 +178,16 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
     __syncthreads();
     for (int t = U - 1; t >= 0; --t) {
         for (int i = tid; i < 32 * 9; i += LS_THREADS) r_s[i] = 0.f;
+        // saved forward values of this step: independent of the recurrent gradient, fetched before the product (latency off the critical path)
+        float pgi = 0.f, pgf = 0.f, pgg = 0.f, pgo = 0.f, pc = 0.f, pcp = 0.f, pdo = 0.f;
+        if (cb < B) {
+            const int j = j0 + cj;
+            const float* gs = gates_save + ((long long)t * Bt + cb) * G4 + j;
+            pgi = __ldg(gs); pgf = __ldg(gs + H); pgg = __ldg(gs + 2 * H); pgo = __ldg(gs + 3 * H);
+            pc = __ldg(cs + ((long long)t * Bt + cb) * H + j);
+            pcp = t > 0 ? __ldg(cs + ((long long)(t - 1) * Bt + cb) * H + j) : 0.f;
+            pdo = to_f32<T>(dout[((long long)cb * U + t) * H + j]);
+        }
         if (t < U - 1) {
             const __nv_bfloat16* src = dG + (long long)(t + 1) * Bt * G4;
             auto issue = [&](int qtr) {                                          // warp 0: lane r copies row r of quarter `qtr`
@@ -212,11 +228,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
         __syncthreads();
         if (cb < B) {
             const int j = j0 + cj;
-            const float* gs = gates_save + ((long long)t * Bt + cb) * G4 + j;
-            const float gi = gs[0], gf = gs[H], gg = gs[2 * H], go = gs[3 * H];
-            const float c = cs[((long long)t * Bt + cb) * H + j];
-            const float cp = t > 0 ? cs[((long long)(t - 1) * Bt + cb) * H + j] : 0.f;
-            const float dh = to_f32<T>(dout[((long long)cb * U + t) * H + j]) + r_s[cb * 9 + cj];
+            const float gi = pgi, gf = pgf, gg = pgg, go = pgo, c = pc, cp = pcp;
+            const float dh = pdo + r_s[cb * 9 + cj];
             const float tc = tanhf(c);
             const float dc = dh * go * (1.f - tc * tc) + dc_state;
             __nv_bfloat16* d = dG + ((long long)t * Bt + cb) * G4 + j;

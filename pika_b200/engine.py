@@ -417,7 +417,7 @@ class AttentionFn(torch.autograd.Function):
             # scores / probabilities never leave the SM (pika_b200/csrc/attention.cu)
             qkv = qkv.contiguous()
             out = _new((B, T, D), like=qkv)
-            lse = torch.empty(B * heads * K.attention_lse_stride(T), dtype=torch.float32, device=qkv.device)
+            lse = torch.zeros(B * heads * K.attention_lse_stride(T), dtype=torch.float32, device=qkv.device)   # pad entries finite
             alpha = 1.0 / math.sqrt(dh)
             K.attention_fwd(qkv, out, lse, heads, alpha, drop_p, seed)
             ctx.save_for_backward(qkv, out, lse)
