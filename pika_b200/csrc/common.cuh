@@ -386,6 +386,28 @@ PK_DEVICE void tma_load_4d_2sm_hint_p(void* smem_dst, const CUtensorMap* m, uint
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol), "r"(pred)
         : "memory");
 }
+PK_DEVICE void tma_store_4d_hint_p(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3, uint64_t pol, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+        "@q cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;\n\t}\n" ::"l"(
+            reinterpret_cast<uint64_t>(m)),
+        "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol), "r"(pred)
+        : "memory");
+}
+PK_DEVICE void tma_reduce_add_4d_p(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+        "@q cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n\t}\n" ::"l"(
+            reinterpret_cast<uint64_t>(m)),
+        "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(pred)
+        : "memory");
+}
+PK_DEVICE void tma_store_commit_p(uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q cp.async.bulk.commit_group;\n\t}\n" ::"r"(pred) : "memory");
+}
+template <int N> PK_DEVICE void tma_store_wait_read_p(uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q cp.async.bulk.wait_group.read %0;\n\t}\n" ::"n"(N), "r"(pred) : "memory");
+}
 PK_DEVICE void umma_bf16_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate, uint32_t pred) {
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t"

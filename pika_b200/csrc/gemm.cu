@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, TWO>::THREADS, 1) gemm_tcgen05_ker
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;          // tile row owned by this thread
         const int et = threadIdx.x - 64 - g * 128;   // 0..127 inside the group
-        const bool store_thread = (et == 0);
+        const uint32_t store_pred = (et == 0) ? 1u : 0u;    // the group's first thread owns the TMA stores (predicated, no divergent region)
         const int bar_stage = 1 + 2 * g, bar_bias = 2 + 2 * g;
         constexpr int GW = CF32 ? 4 : 8;        // columns per 16-byte group
         constexpr int CH = 8 * GW;              // columns per 128-byte staging row
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, TWO>::THREADS, 1) gemm_tcgen05_ker
                 const int nc0 = n0 + ch * CH;
                 if (nc0 >= p.N || m0 >= p.M) break;   // uniform across the 4 warps of the group
                 uint8_t* sbuf = cst + (chunk_ctr & 1) * C_STAGE_BYTES;
-                if (store_thread) tma_store_wait_read<1>();     // the buffer used two chunks ago is free
+                tma_store_wait_read_p<1>(store_pred);           // the buffer used two chunks ago is free
                 named_bar_sync(bar_stage, 128);
                 uint8_t* srow = sbuf + row * 128;
                 auto do_group = [&](const uint32_t (&rr)[GW], const int gq) {
@@ -375,11 +375,9 @@ __global__ void __launch_bounds__(GemmCfg<BN, TWO>::THREADS, 1) gemm_tcgen05_ker
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(bar_stage, 128);
-                if (store_thread) {
-                    if (p.c_accumulate) tma_reduce_add_4d(&p.c, sbuf, nc0, m0, zb0, zb1);
-                    else tma_store_4d_hint(&p.c, sbuf, nc0, m0, zb0, zb1, p.pol_c);
-                    tma_store_commit();
-                }
+                if (p.c_accumulate) tma_reduce_add_4d_p(&p.c, sbuf, nc0, m0, zb0, zb1, store_pred);
+                else tma_store_4d_hint_p(&p.c, sbuf, nc0, m0, zb0, zb1, p.pol_c, store_pred);
+                tma_store_commit_p(store_pred);
                 ++chunk_ctr;
             }
             // a group whose columns lie entirely beyond N contributes an empty partial (max = -inf, sum = 0), which the merge ignores
@@ -390,7 +388,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, TWO>::THREADS, 1) gemm_tcgen05_ker
             __syncwarp();
             if (lane == 0) { if (rank == 0) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_remote(&tmem_empty[acc], 0); }
         }
-        if (store_thread) tma_store_wait<0>();
+        if (store_pred) tma_store_wait<0>();
     }
 
     tc_fence_before();

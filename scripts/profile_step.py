@@ -45,3 +45,22 @@ tot = sum(v[1] for v in agg.values())
 print("total kernel us per step: %.1f" % (tot / 2))
 for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:45]:
     print("%9.1f us %5.1f%% n=%5d  %s" % (t / 2, 100 * t / tot, c // 2, k[:100]))
+
+# ---- idle gaps on the stream: time between the end of one kernel and the start of the next (two profiled steps)
+evs = []
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        tr = ev.time_range
+        evs.append((tr.start, tr.end, re.sub(r"\(.*", "", ev.name).replace("void ", "").replace("pk::", "")[:60]))
+evs.sort()
+gaps = collections.defaultdict(lambda: [0, 0.0])
+tot_gap, span = 0.0, (evs[-1][1] - evs[0][0]) if evs else 0.0
+for (s0, e0, n0), (s1, e1, n1) in zip(evs, evs[1:]):
+    g_ = s1 - e0
+    if g_ > 1.0:
+        tot_gap += g_
+        gaps[(n0, n1)][0] += 1
+        gaps[(n0, n1)][1] += g_
+print("\nstream span %.1f us for 2 steps, idle between kernels %.1f us (%.1f us per step)" % (span, tot_gap, tot_gap / 2))
+for (n0, n1), (c, t) in sorted(gaps.items(), key=lambda x: -x[1][1])[:25]:
+    print("%8.1f us n=%4d  after %-45s before %s" % (t / 2, c // 2 or c, n0[:45], n1[:45]))
