@@ -175,6 +175,11 @@ int pk_layernorm_bwd(const void* dy, const void* x, void* dx, int dtype, long lo
  * (trainer/model/modules/multi_headed_attn.py:220-221): S f32 [rows, ld_s] -> P, Pd=dropout(P) [rows, ld_p] */
 int pk_softmax_fwd(const float* S, long long ld_s, void* P, void* Pd, int dtype, long long ld_p, long long rows, int n,
                    float drop_p, uint32_t seed, void* stream);
+/* masked forward (transformer prediction net, trainer/model/rnnt_conv_transformer_lm.py:66-70 + modules/multi_headed_attn.py:214-216):
+ * rows = sequences * heads * q_len; key c of query i = row % q_len is dropped when (causal && c > i) or key_pad[sequence][c] != 0
+ * (key_pad: uint8 [sequences][n] or NULL).  The backward is pk_softmax_bwd (a dropped key has P = 0). */
+int pk_softmax_masked_fwd(const float* S, long long ld_s, void* P, void* Pd, int dtype, long long ld_p, long long rows, int n,
+                          int q_len, int heads, int causal, const uint8_t* key_pad, float drop_p, uint32_t seed, void* stream);
 int pk_softmax_bwd(const float* dPd, long long ld_d, const void* P, long long ld_p, void* dS, int dtype, long long rows,
                    int n, float drop_p, uint32_t seed, void* stream);
 /* nn.Dropout with the counter-based RNG shared with the GEMM epilogue; mask_nz: dx = dy * (y != 0) * scale */

@@ -206,8 +206,13 @@ def decode_batch(sd, enc_out, x_len, beam_size, n_best=1, blk=0, max_len=None, s
     t_idx = torch.zeros(K, B, dtype=torch.long) - 1                                    # :109
     emb_w = sd["embed.weight"]
     blk_sos = torch.full((B * K, 1), blk, dtype=torch.long)
-    _, (h, c) = om.lstm_forward(sd, F.embedding(blk_sos, emb_w))                       # :116
-    h, c = h.clone(), c.clone()
+    xf = "decoder.conv.0.weight" in sd                 # transformer prediction net: the state is its last output row (:117-120)
+    if xf:
+        pad = emb_w.shape[0] - 1                       # embed.padding_idx (-1 -> last row)
+        dec = om.conv_transformer_lm_forward(sd, blk_sos)[:, -1, :].clone()
+    else:
+        _, (h, c) = om.lstm_forward(sd, F.embedding(blk_sos, emb_w))                   # :116
+        h, c = h.clone(), c.clone()
     rows = torch.arange(B * K)
     while not all(b.done() for b in beams):                                            # :123
         inp = torch.stack([b.next_ys[-1] for b in beams]).t()                          # [K, B]
@@ -215,16 +220,25 @@ def decode_batch(sd, enc_out, x_len, beam_size, n_best=1, blk=0, max_len=None, s
         flat = inp.contiguous().view(-1)
         enc_hid = x[rows, t_idx.contiguous().view(-1).clamp(max=Tenc - 1), :]          # :133-134
         nonblk = flat.gt(blk)                                                          # :139
-        if int(nonblk.sum()) > 0:                                                      # :140-150
+        if int(nonblk.sum()) > 0 and xf:                                               # :151-171: the whole partial hypothesis again
+            idx = rows[nonblk].tolist()
+            hyps = [[blk] + beams[k % B].cur_hyp[k // B] for k in idx]
+            lens = [len(hp) for hp in hyps]
+            src = torch.tensor([hp + [pad] * (max(lens) - len(hp)) for hp in hyps], dtype=torch.long)
+            dec[nonblk] = om.conv_transformer_lm_forward(sd, src)[torch.arange(len(idx)), torch.tensor(lens) - 1, :]
+        elif int(nonblk.sum()) > 0:                                                    # :140-150
             _, (hn, cn) = om.lstm_forward(sd, F.embedding(flat[nonblk].view(-1, 1), emb_w), state=(h[:, nonblk], c[:, nonblk]))
             h[:, nonblk], c[:, nonblk] = hn, cn
-        z = torch.cat((enc_hid, h[-1]), -1)                                            # :173
+        z = torch.cat((enc_hid, dec if xf else h[-1]), -1)                             # :173
         out = om.linear(torch.tanh(om.linear(z, sd, "fc1")) * torch.sigmoid(om.linear(z, sd, "fc_gate")), sd, "fc2")
         out = F.log_softmax(sm_scale * out, -1).view(K, B, -1)                         # :177-178
         for j, b in enumerate(beams):                                                  # :181-183
             b.advance(out[:, j], t_idx[:, j], int(x_len[j]))
             pos = b.prev_ks[-1]
-            for e in (h, c):                                                           # _beam_update :188-202
+            if xf:                                                                     # _beam_update :195-200
+                v = dec.view(K, B, -1)[:, j]
+                v.copy_(v.index_select(0, pos))
+            for e in (() if xf else (h, c)):                                           # _beam_update :188-194
                 v = e.view(e.shape[0], K, B, -1)[:, :, j]
                 v.copy_(v.index_select(1, pos))
             t_idx[:, j] = t_idx[:, j].index_select(0, pos)

@@ -50,9 +50,9 @@ def tdnn(x, sd, name, dil, stride):
     return y
 
 
-def mha(x, sd, name, heads):
-    """MultiHeadedAttention.forward, self-attention, no mask, no cache, no dropout
-    (trainer/model/modules/multi_headed_attn.py:180-184, 199-207, 212-213, 220-223, 231-241)."""
+def mha(x, sd, name, heads, mask=None):
+    """MultiHeadedAttention.forward, self-attention, optional mask [B,T,T] (True = dropped key), no cache, no dropout
+    (trainer/model/modules/multi_headed_attn.py:180-184, 199-207, 212-216, 220-223, 231-241)."""
     B, T, D = x.shape
     dh = D // heads
 
@@ -64,15 +64,17 @@ def mha(x, sd, name, heads):
     q = shape(linear(x, sd, name + ".linear_query"))
     q = q / math.sqrt(dh)                                  # scale BEFORE QK^T (:205)
     scores = torch.matmul(q, k.transpose(2, 3)).float()
+    if mask is not None:
+        scores = scores.masked_fill(mask.unsqueeze(1), -1e18)   # :214-216
     attn = torch.softmax(scores, dim=-1)
     ctx = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, T, D)
     return linear(ctx, sd, name + ".final_linear")
 
 
-def transformer_layer(x, sd, name, heads):
+def transformer_layer(x, sd, name, heads, mask=None):
     """TransformerEncoderLayer.forward (trainer/model/modules/transformer.py:85-100) +
     PositionwiseFeedForward.forward (trainer/model/modules/position_ffn.py:27-39); dropout off."""
-    h = mha(layernorm(x, sd, name + ".layer_norm"), sd, name + ".self_attn", heads) + x
+    h = mha(layernorm(x, sd, name + ".layer_norm"), sd, name + ".self_attn", heads, mask) + x
     ff = name + ".feed_forward"
     inter = F.relu(linear(layernorm(h, sd, ff + ".layer_norm"), sd, ff + ".w_1"))
     return linear(inter, sd, ff + ".w_2") + h
@@ -131,10 +133,35 @@ def lstm_forward(sd, x, prefix="decoder.", layers=2, state=None):
     return inp, (torch.stack(hs), torch.stack(cs))
 
 
+def conv_transformer_lm_forward(sd, src, prefix="decoder.", heads=8):
+    """Net.forward of the transformer prediction net (trainer/model/rnnt_conv_transformer_lm.py:59-80), dropout off.
+    src [B,L] int64 -> [B,L,output_dim].  The embedding table is the transducer's ``embed`` (trainer/model/transducer.py:63);
+    its padding_idx -1 resolves to the last row, whose id also marks padding keys (:66-68)."""
+    emb_w = sd["embed.weight"]
+    pad = emb_w.shape[0] - 1
+    out = F.embedding(src, emb_w, padding_idx=pad)
+    B, L = src.shape
+    pad_mask = src.eq(pad).unsqueeze(1).expand(B, L, L)                                    # :66-68
+    causal = torch.triu(torch.ones(L, L, dtype=torch.bool), diagonal=1).unsqueeze(0)      # :82-87
+    mask = pad_mask | causal                                                               # :69-70
+    l = 0
+    while prefix + "conv.%d.weight" % l in sd:
+        w, b = sd[prefix + "conv.%d.weight" % l], sd[prefix + "conv.%d.bias" % l]           # [N, C, 5]
+        kw = w.shape[2]
+        y = F.conv1d(out.transpose(1, 2), w, b, padding=kw - 1)[:, :, :-(kw - 1)]         # causal: drop the right overhang (:74)
+        out = F.relu(y).transpose(1, 2)
+        out = transformer_layer(out, sd, prefix + "transformer.%d" % l, heads, mask)       # :76
+        l += 1
+    return linear(layernorm(out, sd, prefix + "layer_norm"), sd, prefix + "linear_out")    # :77-78
+
+
 def prednet_forward(sd, y, blank=0):
-    """SOS prepend + embedding + LSTM (trainer/model/transducer.py:90-95).  y [B,U] int64 -> [B,U+1,H]."""
+    """SOS prepend + embedding + LSTM (trainer/model/transducer.py:90-95), or the transformer prediction net when the
+    state dict holds one (:96-97).  y [B,U] int64 -> [B,U+1,H]."""
     sos = torch.full((y.shape[0], 1), blank, dtype=torch.long)
     yy = torch.cat((sos, y.long()), 1)
+    if "decoder.conv.0.weight" in sd:
+        return conv_transformer_lm_forward(sd, yy)
     emb = F.embedding(yy, sd["embed.weight"], padding_idx=sd["embed.weight"].shape[0] - 1)   # padding row: no gradient
     return lstm_forward(sd, emb)[0]
 

@@ -389,7 +389,12 @@ PK_DEVICE void ld8f(const float* p, float (&f)[8]) {
 template <typename T, int SM_CH>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, long long ld_s, T* __restrict__ P,
                                                           T* __restrict__ Pd, long long ld_p, long long rows, int n,
-                                                          uint32_t drop_thresh, float drop_scale, uint32_t seed) {
+                                                          uint32_t drop_thresh, float drop_scale, uint32_t seed, int q_len = 0,
+                                                          int heads = 1, int causal = 0, const uint8_t* __restrict__ key_pad = nullptr) {
+    // masked form (q_len > 0; the transformer prediction net, trainer/model/rnnt_conv_transformer_lm.py:66-70): row r is query
+    // i = r % q_len of sequence r / (heads * q_len); key c is dropped when c > i (causal) or key_pad[seq, c] != 0.  A dropped score
+    // becomes -inf where the reference fills -1e18 (multi_headed_attn.py:214-216): both give probability exactly 0 as long as one key
+    // survives, which the causal diagonal guarantees.
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
@@ -397,13 +402,19 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
         const float* sr = S + r * ld_s;
         float v[SM_CH][8];
         float m = -INFINITY;
+        int lim = n;
+        const uint8_t* kp = nullptr;
+        if (q_len > 0) {
+            if (causal) lim = min(n, (int)(r % q_len) + 1);
+            if (key_pad) kp = key_pad + (r / ((long long)heads * q_len)) * n;
+        }
 #pragma unroll
         for (int k = 0; k < SM_CH; ++k) {
             const int c0 = lane * 8 + k * 256;
             if (c0 < (int)ld_p) ld8f(sr + c0, v[k]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                if (c0 + e >= n) v[k][e] = -INFINITY;
+                if (c0 + e >= lim || (kp && kp[c0 + e])) v[k][e] = -INFINITY;
                 m = fmaxf(m, v[k][e]);
             }
         }
@@ -914,6 +925,18 @@ extern "C" int pk_softmax_fwd(const float* S, long long ld_s, void* P, void* Pd,
     const float sc = drop_scale16_of(th);
     if (ld_p <= 1024) { PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T, 4><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed))); }
     else { PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T, 8><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed))); }
+    DONE();
+}
+extern "C" int pk_softmax_masked_fwd(const float* S, long long ld_s, void* P, void* Pd, int dtype, long long ld_p, long long rows, int n,
+                                     int q_len, int heads, int causal, const uint8_t* key_pad, float drop_p, uint32_t seed, void* stream) {
+    PK_CHECK_ARG(rows > 0 && n > 0 && ld_p >= n && ld_s >= ld_p && ld_p <= 2048 && ld_p % 8 == 0 && ld_s % 8 == 0, "softmax rows: ld % 8 == 0, <= 2048 wide");
+    PK_CHECK_ARG(q_len > 0 && heads > 0 && rows % ((long long)heads * q_len) == 0, "masked softmax: rows = sequences * heads * q_len");
+    PK_CHECK_ARG(causal || key_pad, "masked softmax without a mask: use pk_softmax_fwd");
+    const int grid = grid_for(rows, 8);
+    const uint32_t th = drop_thresh16_of(drop_p);
+    const float sc = drop_scale16_of(th);
+    if (ld_p <= 1024) { PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T, 4><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed, q_len, heads, causal, key_pad))); }
+    else { PK_DISPATCH_T(dtype, (softmax_fwd_kernel<T, 8><<<grid, 256, 0, STREAM(stream)>>>(S, ld_s, (T*)P, (T*)Pd, ld_p, rows, n, th, sc, seed, q_len, heads, causal, key_pad))); }
     DONE();
 }
 extern "C" int pk_softmax_bwd(const float* dPd, long long ld_d, const void* P, long long ld_p, void* dS, int dtype, long long rows,

@@ -40,7 +40,7 @@ class _Workspace:
         self.B, self.Tcap, self.Scap, self.adt, self.dev = B, Tcap, Scap, adt, dev
         H = m.fc1.weight.shape[0]
         V = m.fc2.weight.shape[0]
-        L = m.decoder.num_layers
+        L = m.decoder.num_layers if dec.xf is False else 0         # transformer prediction net: no recurrent state (see _xf_states)
         E = m.embed.weight.shape[1]
         self.H, self.V, self.L, self.E = H, V, L, E
         self.ldx = (E + 7) // 8 * 8
@@ -58,8 +58,8 @@ class _Workspace:
         self.fin_count, self.eos_top, self.done, self.not_done = i32(B), i32(B), i32(B), i32(1)
         self.scores = f32(B, Kb)
         self.t_idx, self.t_alt = i32(rows), i32(rows)
-        self.h = torch.zeros(L, rows, H, dtype=adt, device=dev)
-        self.c = f32(L, rows, H)
+        self.h = torch.zeros(max(L, 1), rows, H, dtype=adt, device=dev)
+        self.c = f32(max(L, 1), rows, H)
         self.h_alt, self.c_alt = torch.empty_like(self.h), torch.empty_like(self.c)
         self.enc_hid = torch.empty(rows, H, dtype=adt, device=dev)
         self.x_emb = torch.zeros(rows, self.ldx, dtype=adt, device=dev)
@@ -103,7 +103,7 @@ class _Workspace:
             dst = bufs if rows is None else [b[rows[0]:rows[1]] for b in bufs]
             K.cast_split(mat, dst[0], dst[1] if len(dst) > 1 else None, cols_pad=cols_pad or mat.shape[1])
         H = self.H
-        for l in range(self.L):
+        for l in range(self.L):                          # (no LSTM layers with the transformer prediction net)
             put(self.w_ih[l], getattr(lstm, "weight_ih_l%d" % l), cols_pad=self.ldx if l == 0 else None)
             put(self.w_hh[l], getattr(lstm, "weight_hh_l%d" % l))
             K.add(getattr(lstm, "bias_ih_l%d" % l).detach(), getattr(lstm, "bias_hh_l%d" % l).detach(), self.bsum[l])
@@ -145,8 +145,9 @@ class TransducerDecoder():
         for name in ("las_rescorer", "las_rescorer_bw", "bilas_rescorer"):
             if args is not None and getattr(args, name, None) is not None:
                 raise NotImplementedError("pika_b200: LAS rescoring is outside the hot path")
-        if model.decoder_type != "rnn":
-            raise NotImplementedError("pika_b200: only the LSTM prediction net is supported")
+        self.xf = model.decoder_type != "rnn"            # convolutional-transformer prediction net (decoder/transducer_decoder.py:117-120,151-171)
+        if self.xf and lm_scorer is not None:
+            raise NotImplementedError("pika_b200: FST fusion is wired to the LSTM prediction net only")
         self._ws = None
         self.last_replays = self.kernels_per_replay = 0
 
@@ -159,9 +160,29 @@ class TransducerDecoder():
             ws = self._ws = _Workspace(self, B, max(Tenc, ws.Tcap if same else 0), max(S, ws.Scap if same else 0), adt, dev)
         return ws
 
-    def _beam_step(self, ws, h, c, t_idx, h_out, c_out, t_out):
+    def _xf_states(self, ws, par):
+        """prediction-net output for every beam row from its current partial hypothesis (transformer branch,
+        decoder/transducer_decoder.py:117-120,151-171).  The reference re-runs the whole history through the network for the rows that
+        just emitted a label and keeps / reorders the stored output row otherwise; the network is causal and masks padding keys, so a
+        row's output at its last position depends on its own history only -- recomputing every row from the hypothesis buffers
+        (which ``pk_beam_advance`` already reorders) gives the same values and needs no state reorder."""
+        m, rows = self.model, ws.rows
+        hl = ws.hyp_len[par].reshape(rows)
+        lmax = int(hl.max().item())
+        pad = m.embed.padding_idx
+        src = torch.full((rows, lmax + 1), pad, dtype=torch.long, device=ws.dev)
+        src[:, 0] = self.blk
+        if lmax > 0:
+            tok = ws.hyp_tok[par].reshape(rows, -1)[:, :lmax].long()
+            keep = torch.arange(lmax, device=ws.dev)[None, :] < hl[:, None]
+            src[:, 1:] = torch.where(keep, tok, torch.full_like(tok, pad))
+        out = engine.conv_transformer_lm_forward_act(m.decoder, src)                       # [rows, lmax + 1, H]
+        return out[torch.arange(rows, device=ws.dev), hl.long()].contiguous()
+
+    def _beam_step(self, ws, h, c, t_idx, h_out, c_out, t_out, par=None):
         """one iteration of `while not all(b.done() ...)` (decoder/transducer_decoder.py:123-186) for the whole batch;
-        graph-capturable: no host reads, no step-dependent arguments (the kernels read the step from ``step_ctx``)"""
+        graph-capturable with the LSTM prediction net: no host reads, no step-dependent arguments (the kernels read the step from
+        ``step_ctx``).  ``par`` (transformer prediction net only): parity of the step, selects the live hypothesis buffers."""
         m, Kb, blk = self.model, self.beam_size, self.blk
         P, st = K._P, K._stream
         H, V, L, rows = ws.H, ws.V, ws.L, ws.rows
@@ -174,7 +195,8 @@ class TransducerDecoder():
             engine.gemm_parts([engine.stage_act(h[l])], [ws.w_hh[l]], ws.gates, accumulate=True, k_splits=1)
             check(lib.pk_beam_lstm_cell(P(ws.gates), P(ws.next_ys), P(ws.step_ctx), blk, P(h[l]), dt, P(c[l]), rows, H, st()), "pk_beam_lstm_cell")
             xin = h[l]
-        engine.gemm_parts([engine.stage_act(ws.enc_hid), engine.stage_act(h[L - 1])],
+        dec_hid = self._xf_states(ws, par) if self.xf else h[L - 1]
+        engine.gemm_parts([engine.stage_act(ws.enc_hid), engine.stage_act(dec_hid)],
                           [[p[:, :H] for p in ws.wx], [p[:, H:] for p in ws.wx]], ws.pre, bias=ws.bx)
         check(lib.pk_beam_gate(P(ws.pre), P(ws.hj), K._dt(ws.hj), rows, H, st()), "pk_beam_gate")
         engine.gemm_parts([engine.stage_act(ws.hj)], [ws.w2], ws.logits[:, :V], bias=ws.b2)
@@ -215,6 +237,8 @@ class TransducerDecoder():
         ws.stage(self)
         ws.reset(self, enc, x_len, ml_list)
 
+        if self.xf:
+            return self._decode_loop_xf(ws, enc, B)
         # initial decoder state = LSTM(embed(blk)) from zeros (decoder/transducer_decoder.py:116)
         ws.x_emb.zero_()
         ws.x_emb[:, :ws.E] = m.embed.weight.detach()[blk].to(ws.adt)
@@ -252,10 +276,24 @@ class TransducerDecoder():
                 self.last_replays += 1
             if int(ws.not_done.item()) == 0:                                    # `while not all(b.done() for b in beam)`
                 break
-        step = int(ws.step_ctx[0].item())                                       # beam steps actually executed
         if ws.lm is not None and int(ws.lm["err"].item()) != 0:
             raise RuntimeError("pika_b200: an FST state set outgrew lm_max_states=%d active states per beam" % self.lm_max_states)
+        return self._extract(ws, enc, B)
 
+    def _decode_loop_xf(self, ws, enc, B):
+        """beam loop with the transformer prediction net: issued step by step from the host (the history length, hence every shape
+        of the prediction net, changes with the step, so there is no fixed graph to replay)"""
+        bufs = ((ws.t_idx, ws.t_alt), (ws.t_alt, ws.t_idx))
+        for i in range(ws.Scap - 1):
+            t_in, t_out = bufs[i & 1]
+            self._beam_step(ws, ws.h, ws.c, t_in, ws.h, ws.c, t_out, par=i & 1)
+            if int(ws.not_done.item()) == 0:                                    # `while not all(b.done() for b in beam)`
+                break
+        self.last_replays = 0
+        return self._extract(ws, enc, B)
+
+    def _extract(self, ws, enc, B):
+        step = int(ws.step_ctx[0].item())                                       # beam steps actually executed
         # (4) extract: sort_finished + get_hyp on the host, once
         ny, pk = ws.next_ys[:step + 1].cpu().numpy(), ws.prev_ks[:step].cpu().numpy()
         fc = ws.fin_count.cpu().numpy()

@@ -120,6 +120,28 @@ def stage_weight(params, cols_pad=None, scale=None):
     return parts
 
 
+def stage_conv1d_weight(weight, ld):
+    """nn.Conv1d weight [N, C, Kw] -> staged bf16 parts of the tap-major matrix [N, Kw * ld] (tap k at columns [k*ld, k*ld + C),
+    zero padding up to the activation pitch ``ld``): the B operand of the causal convolution written as one GEMM over
+    overlapping (Toeplitz) activation rows.  Cached like ``stage_weight``."""
+    key = (id(weight), _PRECISION, "conv1d", ld)
+    stamp = (weight._version, _WEIGHT_EPOCH, weight.data_ptr())
+    hit = _wcache.get(key)
+    if hit is not None and hit[0] == stamp and _same_objects(hit[2], [weight]):
+        return hit[1]
+    N, C, Kw = weight.shape
+    mat = torch.zeros(N, Kw, ld, dtype=torch.float32, device=weight.device)
+    mat[:, :, :C] = weight.detach().permute(0, 2, 1)
+    mat = mat.view(N, Kw * ld)
+    hi = torch.empty(N, Kw * ld, dtype=torch.bfloat16, device=weight.device)
+    lo = torch.empty_like(hi) if _PRECISION == "fp32" else None
+    K.cast_split(mat, hi, lo)
+    parts = [hi] if lo is None else [hi, lo]
+    _prune_wcache()
+    _wcache[key] = (stamp, parts, (weakref.ref(weight),))
+    return parts
+
+
 # opt-in: same-box A/B of the full step showed no gain (88.2 vs 87.9 ms) although isolated dgrads are 5-18 % faster with a
 # K-major B on random data; the extra transposes cancel it (profiles/r01_notes.md)
 _DGRAD_KMAJOR = os.environ.get("PK_DGRAD_KMAJOR", "0") != "0"
@@ -352,6 +374,58 @@ class TdnnFn(torch.autograd.Function):
         return dx, None, None, None, None, None
 
 
+class CausalConvFn(torch.autograd.Function):
+    """relu(Conv1d(C, N, Kw, padding=Kw-1)(x)[..., :-(Kw-1)]) on [B,T,ld] (ld >= C, pad columns zero) -- the causal convolution of
+    the transformer prediction net (trainer/model/rnnt_conv_transformer_lm.py:36-46, 74-75).
+    Forward: ONE GEMM.  Row (b, t) of the im2col matrix is the window x[b, t-Kw+1 .. t, :], which is contiguous in a left-padded
+    [B, T+Kw-1, ld] buffer, so the A operand is an overlapping strided view of that buffer (row pitch ld, K = Kw*ld) and the B
+    operand the tap-major staged weight.  dgrad: Kw accumulated taps with row offsets (rows past T read as zero); wgrad: the same
+    overlapping view read MN-major, one batched-reduction GEMM into the tap-major gradient, permuted into the [N, C, Kw] layout."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        B, T, ld = x.shape
+        N, C, Kw = weight.shape
+        assert ld >= C and ld % 8 == 0
+        xp = _new((B, T + Kw - 1, ld), like=x, zero=True)
+        xp[:, Kw - 1:, :] = x
+        a_parts = [p.as_strided((B, T, Kw * ld), ((T + Kw - 1) * ld, ld, 1)) for p in stage_act(xp)]
+        w_parts = stage_conv1d_weight(weight, ld)
+        y = _new((B, T, N), like=x)
+        gemm_parts([a_parts], [w_parts], y, a_sel=(K.SEL_ZB0, K.SEL_ZERO), b_sel=(K.SEL_ZERO, K.SEL_ZERO), bias=bias.detach(),
+                   act=K.ACT_RELU)
+        ctx.save_for_backward(y)
+        ctx.a_parts, ctx.w_parts, ctx.weight, ctx.bias, ctx.shape = a_parts, w_parts, weight, bias, (B, T, ld, N, C, Kw)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        B, T, ld, N, C, Kw = ctx.shape
+        dpre = torch.empty_like(y)
+        K.mask_nz(dy.contiguous(), y, dpre, 1.0)
+        d_parts = stage_act(dpre)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # dx[t] = sum_k dpre[t + Kw-1-k] W_k; at most 9 (A,B) pairs per launch: 3 taps in the split-bf16 mode, all of them in bf16
+            per = 3 if len(d_parts) > 1 else Kw
+            dx = _new((B, T, ld), dtype=torch.float32 if len(d_parts) > 1 else None, like=y)
+            for k0 in range(0, Kw, per):
+                ks = list(range(k0, min(Kw, k0 + per)))
+                b_taps, wmn = [], True
+                for k in ks:
+                    bt, wmn = dgrad_b(ctx.w_parts, cols=(k * ld, (k + 1) * ld))
+                    b_taps.append(bt)
+                gemm_parts([d_parts] * len(ks), b_taps, dx, b_mn=wmn, a_sel=(K.SEL_ZB0, K.SEL_ZERO), b_sel=(K.SEL_ZERO, K.SEL_ZERO),
+                           a_row_off=[Kw - 1 - k for k in ks], accumulate=k0 > 0)
+        gw = torch.empty(N, Kw * ld, dtype=torch.float32, device=y.device)
+        gemm_parts([d_parts], [ctx.a_parts], gw, a_mn=True, b_mn=True, a_sel=(K.SEL_KZ, K.SEL_ZERO), b_sel=(K.SEL_KZ, K.SEL_ZERO),
+                   kz_count=B)
+        grad_of(ctx.weight).copy_(gw.view(N, Kw, ld)[:, :, :C].permute(0, 2, 1))
+        K.colsum(dpre.view(B * T, N), grad_of(ctx.bias))
+        return dx, None, None
+
+
 class BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bn, train, _w=None, _b=None, relu_input=False):
@@ -404,15 +478,19 @@ _FOLD_MASKS = os.environ.get("PK_FOLD_MASKS", "1") != "0"
 
 
 class AttentionFn(torch.autograd.Function):
-    """Unmasked multi-head self-attention on a fused QKV tensor [B,T,3D] (q | k | v blocks):
-    softmax((Q/sqrt(d)) K^T) -> dropout -> V   (trainer/model/modules/multi_headed_attn.py:199-223)."""
+    """Multi-head self-attention on a fused QKV tensor [B,T,3D] (q | k | v blocks):
+    softmax((Q/sqrt(d)) K^T [masked]) -> dropout -> V   (trainer/model/modules/multi_headed_attn.py:199-223).
+    Unmasked (the encoder): the fused tcgen05 kernels.  ``causal`` / ``key_pad`` (uint8 [B,T], 1 = padding key; the transformer
+    prediction net, trainer/model/rnnt_conv_transformer_lm.py:66-70): batched GEMMs + the masked softmax kernel (short label
+    sequences; the mask only enters the forward softmax -- a dropped key has probability 0, so its dS is 0 as well)."""
 
     @staticmethod
-    def forward(ctx, qkv, heads, drop_p, seed):
+    def forward(ctx, qkv, heads, drop_p, seed, causal=False, key_pad=None):
         B, T, D3 = qkv.shape
         D = D3 // 3
         dh = D // heads
-        ctx.fused = _FUSED_ATTN and qkv.dtype == torch.bfloat16 and dh == 64
+        masked = causal or key_pad is not None
+        ctx.fused = _FUSED_ATTN and qkv.dtype == torch.bfloat16 and dh == 64 and not masked
         if ctx.fused:
             # scores / probabilities never leave the SM (pika_b200/csrc/attention.cu)
             qkv = qkv.contiguous()
@@ -435,7 +513,10 @@ class AttentionFn(torch.autograd.Function):
         gemm_parts([q], [k], S[:, :, :, :T], alpha=alpha)
         P = _new((B, heads, T, Tp), like=qkv)
         Pd = _new((B, heads, T, Tp), like=qkv) if drop_p > 0 else P
-        K.softmax_fwd(S, P, Pd, T, drop_p, seed)
+        if masked:
+            K.softmax_masked_fwd(S, P, Pd, T, T, heads, causal, key_pad, drop_p, seed)
+        else:
+            K.softmax_fwd(S, P, Pd, T, drop_p, seed)
         del S
         out = _new((B, T, D), like=qkv)
         pd_parts = stage_act(Pd)
@@ -452,7 +533,7 @@ class AttentionFn(torch.autograd.Function):
             B, T, D, heads, dh, _, drop_p, seed, alpha = ctx.meta
             dqkv = torch.empty_like(qkv)
             K.attention_bwd(qkv, out, dout.contiguous(), lse, dqkv, heads, alpha, drop_p, seed)
-            return dqkv, None, None, None
+            return dqkv, None, None, None, None, None
         qkv, P = ctx.saved_tensors
         B, T, D, heads, dh, Tp, drop_p, seed, alpha = ctx.meta
         dout = dout.contiguous()
@@ -476,7 +557,7 @@ class AttentionFn(torch.autograd.Function):
         # dQ = alpha * dS K ; dK = alpha * dS^T Q
         gemm_parts([ds_parts], [k], head_view(dqkv, 0), b_mn=True, alpha=alpha)
         gemm_parts([ds_parts], [q], head_view(dqkv, 1), a_mn=True, b_mn=True, alpha=alpha)
-        return dqkv, None, None, None
+        return dqkv, None, None, None, None, None
 
 
 class EmbeddingFn(torch.autograd.Function):
@@ -785,14 +866,14 @@ def _to_act(x):
     return x.float()
 
 
-def transformer_layer(layer, x2, B, T, training):
-    """x2 [B*T, D] -> [B*T, D]   (pre-LN attention block + position-wise FFN)."""
+def transformer_layer(layer, x2, B, T, training, causal=False, key_pad=None):
+    """x2 [B*T, D] -> [B*T, D]   (pre-LN attention block + position-wise FFN); ``causal`` / ``key_pad``: see AttentionFn."""
     att, ff = layer.self_attn, layer.feed_forward
     p = _drop(layer.dropout_p, training)
     ln = LayerNormFn.apply(x2, layer.layer_norm, layer.layer_norm.weight, layer.layer_norm.bias)
     qkv = linear(ln, [att.linear_query.weight, att.linear_keys.weight, att.linear_values.weight],
                  [att.linear_query.bias, att.linear_keys.bias, att.linear_values.bias])
-    ctxv = AttentionFn.apply(qkv.view(B, T, -1), att.head_count, p, _next_seed() if p > 0 else 0)
+    ctxv = AttentionFn.apply(qkv.view(B, T, -1), att.head_count, p, _next_seed() if p > 0 else 0, causal, key_pad)
     h1 = linear(ctxv.view(B * T, -1), att.final_linear.weight, att.final_linear.bias, drop_p=p, residual=x2)
     ln2 = LayerNormFn.apply(h1, ff.layer_norm, ff.layer_norm.weight, ff.layer_norm.bias)
     fold = _FOLD_MASKS and ln2.dtype == torch.bfloat16
@@ -834,6 +915,8 @@ def prednet_forward_act(model, y):
     B, U = y.shape
     sos = torch.zeros(B, 1, dtype=torch.long, device=y.device)
     yy = torch.cat((sos, y.long()), dim=1).contiguous()
+    if getattr(model, "decoder_type", "rnn") != "rnn":
+        return conv_transformer_lm_forward_act(model.decoder, yy)                  # trainer/model/transducer.py:96-97
     E = model.embed.weight.shape[1]
     ld = (E + 7) // 8 * 8
     h = EmbeddingFn.apply(yy, model.embed, ld, model.embed.weight).view(B, U + 1, ld)
@@ -845,6 +928,27 @@ def prednet_forward_act(model, y):
         if p > 0 and l < lstm.num_layers - 1:
             h = DropoutFn.apply(h, p, _next_seed())
     return h
+
+
+def conv_transformer_lm_forward_act(dec, src):
+    """Transformer prediction net (trainer/model/rnnt_conv_transformer_lm.py:59-80): src [B,L] int64 (SOS already prepended) ->
+    [B,L,output_dim].  Embedding -> num_layers x (causal Conv1d(k=5) + ReLU -> pre-LN transformer layer under the causal +
+    padding-key mask) -> LayerNorm -> linear_out."""
+    if getattr(dec, "max_relative_positions", 0) > 0:
+        raise NotImplementedError("pika_b200: relative position embeddings (max_relative_positions > 0) are not on the hot path")
+    B, L = src.shape
+    emb = dec.embeddings
+    ld = (emb.weight.shape[1] + 7) // 8 * 8
+    src = src.contiguous()
+    h = EmbeddingFn.apply(src, emb, ld, emb.weight).view(B, L, ld)
+    key_pad = src.eq(emb.padding_idx).to(torch.uint8).contiguous() if emb.padding_idx is not None else None     # :66-68
+    training = dec.training
+    for conv, layer in zip(dec.conv, dec.transformer):
+        assert conv.kernel_size[0] - 1 == conv.padding[0] and conv.dilation[0] == 1 and conv.stride[0] == 1
+        h = CausalConvFn.apply(h, conv.weight, conv.bias)                          # :74-75
+        h = transformer_layer(layer, h.view(B * L, -1), B, L, training, causal=True, key_pad=key_pad).view(B, L, -1)
+    hn = LayerNormFn.apply(h.reshape(B * L, -1), dec.layer_norm, dec.layer_norm.weight, dec.layer_norm.bias)
+    return linear(hn, dec.linear_out.weight, dec.linear_out.bias).view(B, L, -1)
 
 
 def transducer_forward(model, x, y, softmax=True):

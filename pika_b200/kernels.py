@@ -237,6 +237,16 @@ def softmax_fwd(S, P, Pd, n, drop_p, seed):
                              _F(drop_p), _U(seed & 0xFFFFFFFF), _stream()), "pk_softmax_fwd")
 
 
+def softmax_masked_fwd(S, P, Pd, n, q_len, heads, causal, key_pad, drop_p, seed):
+    """rows of S = (sequence, head, query); key c of query i is dropped when c > i (causal) or key_pad[sequence, c] != 0"""
+    rows = S.numel() // S.shape[-1]
+    if key_pad is not None:
+        assert key_pad.dtype == torch.uint8 and key_pad.is_contiguous() and key_pad.shape[-1] == n
+    check(lib.pk_softmax_masked_fwd(_P(S), _L(S.shape[-1]), _P(P), _P(Pd), _I(_dt(P)), _L(P.shape[-1]), _L(rows), _I(n), _I(q_len),
+                                    _I(heads), _I(int(bool(causal))), _P(key_pad), _F(drop_p), _U(seed & 0xFFFFFFFF), _stream()),
+          "pk_softmax_masked_fwd")
+
+
 def softmax_bwd(dPd, P, dS, n, drop_p, seed):
     rows = P.numel() // P.shape[-1]
     check(lib.pk_softmax_bwd(_P(dPd), _L(dPd.shape[-1]), _P(P), _L(P.shape[-1]), _P(dS), _I(_dt(P)), _L(rows), _I(n),

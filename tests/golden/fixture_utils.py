@@ -35,6 +35,21 @@ def decode_fixture_reinit(m, blank_bias=5.0, s_l=0.15, s_hh=0.04, s_j=0.05, s_o=
     return m
 
 
+def decode_fixture_reinit_xf(m, blank_bias=2.5, s_j=0.05, s_o=0.1, out_scale=6.0, seed=2025):
+    """Same purpose for the transformer prediction net (decoder_type='transformer'): wider embeddings and output projection so
+    the prediction net reacts to its history, wider joint weights, a blank bias.  Conv / attention / FFN weights keep their
+    seeded default initialisation."""
+    gg = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        m.embed.weight.normal_(0, 1, generator=gg)
+        m.decoder.linear_out.weight *= out_scale
+        for l in (m.fc1, m.fc_gate):
+            l.weight.normal_(0, s_j, generator=gg)
+        m.fc2.weight.normal_(0, s_o, generator=gg)
+        m.fc2.bias[0] += blank_bias
+    return m
+
+
 def grad_fingerprint(g, n=384):
     """Compact, position-sensitive summary of a gradient tensor: [sum, abs-sum, l2 norm] followed by n strided samples
     (all elements when the tensor has at most n).  Used to pin whole-model gradients without storing 90 M floats."""

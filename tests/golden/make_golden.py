@@ -195,6 +195,105 @@ def golden_decode_big():
                         dims=np.array([V, B, Tp, beam, nbest]), **cases)
 
 
+def build_ref_model_xf(V, seed=778, embd=100, dec_layers=2):
+    """reference transducer with the convolutional-transformer prediction net (trainer/model/transducer.py:62-68)"""
+    from trainer.model.transducer import Net
+    a = ref_shim.model_args(V, embd_dim=embd, dec_layers=dec_layers)
+    a.decoder_type = "transformer"
+    torch.manual_seed(seed)
+    return Net(a, 240, V)
+
+
+def xf_inputs(seed, B, Tp, H=1024):
+    return np.random.default_rng(seed).standard_normal((B, Tp, H)).astype(np.float32)
+
+
+def golden_model_xf():
+    """Reference model with decoder_type='transformer': prediction net + joint forward and (torchaudio-loss) backward.  The
+    encoder is replaced by seeded outputs (it is pinned by model_small.npz); everything from the embedding to the loss is the
+    reference's own code.  The second utterance's label row ends in padding ids (= V, embed.padding_idx), which exercises the
+    padding-key mask of trainer/model/rnnt_conv_transformer_lm.py:66-70."""
+    import torchaudio
+    V, B, Tp, U = 40, 3, 20, 9
+    m = build_ref_model_xf(V)
+    m.train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    fp = weight_fingerprint(m)
+    g = torch.Generator().manual_seed(99)
+    y = torch.randint(1, V, (B, U), generator=g)
+    ulens = torch.tensor([U, U - 3, U - 5], dtype=torch.int32)
+    for b in range(B):
+        y[b, int(ulens[b]):] = V
+    enc = torch.from_numpy(xf_inputs(707, B, Tp)).requires_grad_(True)
+    tl = torch.tensor([Tp, Tp - 4, Tp - 7], dtype=torch.int32)
+    sos = torch.zeros(B, 1).long()
+    pred = m.decoder(torch.cat((sos, y), dim=1))                       # trainer/model/transducer.py:96-97
+    T_, U1 = enc.size(1), pred.size(1)
+    out = torch.cat((enc.unsqueeze(2).expand(-1, -1, U1, -1), pred.unsqueeze(1).expand(-1, T_, -1, -1)), dim=-1)
+    logits = m.fc2(torch.tanh(m.fc1(out)) * torch.sigmoid(m.fc_gate(out)))
+    lp = F.log_softmax(logits, -1)
+    yl = y.clone()
+    yl[yl == V] = 0                                                     # label values past label_lens are never read by the loss
+    costs = torchaudio.functional.rnnt_loss(lp, yl.int(), tl, ulens, blank=0, reduction="none", fused_log_softmax=False)
+    costs.sum().backward()
+    from fixture_utils import grad_fingerprint
+    res = dict(y=y.numpy().astype(np.int64), ulens=ulens.numpy(), tlens=tl.numpy(), pred=pred.detach().numpy(),
+               logits=logits.detach().numpy()[:, ::3, :, :], costs=costs.detach().numpy(), denc=grad_fingerprint(enc.grad, 512),
+               dims=np.array([V, B, Tp, U]), seed=np.array(707))
+    for k, v in fp.items():
+        if not k.startswith("encoder."):
+            res["w_" + k] = v
+    for k, p in m.named_parameters():
+        if not k.startswith("encoder."):
+            res["gs_" + k] = grad_fingerprint(p.grad if p.grad is not None else torch.zeros_like(p), 512)
+    np.savez_compressed(os.path.join(HERE, "model_xf.npz"), **res)
+    print("model_xf: costs", costs.tolist(), "pred", tuple(pred.shape))
+
+
+def golden_decode_xf():
+    """Reference decode_batch with the transformer prediction net (decoder/transducer_decoder.py:117-120,151-171,195-200), beam 4
+    and 8, on seeded encoder outputs.  The reference builds ``torch.cuda.LongTensor`` in that branch unconditionally (:166); for
+    this CPU run the name is pointed at ``torch.LongTensor`` (an environment repair, no arithmetic involved)."""
+    import types
+    ref_shim.load_beam_module()
+    from decoder.transducer_decoder import TransducerDecoder
+    import decoder.beam_transducer as bt
+    from fixture_utils import decode_fixture_reinit_xf
+    V, B, Tp = 40, 4, 24
+    m = build_ref_model_xf(V)
+    m.eval()
+    decode_fixture_reinit_xf(m)
+    enc_t = torch.from_numpy(xf_inputs(808, B, Tp))
+
+    class FixedEncoder(torch.nn.Module):
+        def forward(self, x):
+            return enc_t
+
+    m.encoder = FixedEncoder()
+    tl = torch.tensor([24, 21, 17, 9])
+    cases = {}
+    saved = torch.cuda.LongTensor
+    torch.cuda.LongTensor = torch.LongTensor
+    try:
+        for name, beam, nbest in [("b4n2", 4, 2), ("b8n4", 8, 4)]:
+            dargs = types.SimpleNamespace(las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None, nonblk_reward=0.0)
+            dec = TransducerDecoder(m, B, beam, n_best=nbest, blk=0, global_scorer=bt.GlobalScorer(), sm_scale=1.0, cuda=False,
+                                    beam_prune=True, args=dargs)
+            with torch.no_grad():
+                ret, _ = dec.decode_batch(torch.zeros(B, 1, 240), tl, max_len=[int(t) + 30 for t in tl])
+            for b in range(B):
+                for n in range(nbest):
+                    cases["%s_pred_%d_%d" % (name, b, n)] = np.array([int(t) for t in ret["predictions"][b][n]], np.int64)
+                    cases["%s_score_%d_%d" % (name, b, n)] = np.array(float(ret["scores"][b][n]))
+            print("decode_xf", name, [len(cases["%s_pred_%d_0" % (name, b)]) for b in range(B)],
+                  [cases["%s_pred_%d_0" % (name, b)].tolist() for b in range(2)], [float(ret["scores"][b][0]) for b in range(B)])
+    finally:
+        torch.cuda.LongTensor = saved
+    np.savez_compressed(os.path.join(HERE, "decode_xf.npz"), seed=np.array(808), tlens=tl.numpy(), dims=np.array([V, B, Tp]), **cases)
+
+
 class _FakeFst:
     """the slice of the kaldi.fstext VectorFst interface decoder/sorted_matcher.py uses, over an in-memory arc table"""
 
@@ -521,6 +620,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["rnnt", "frontend", "specaug", "encoder", "model", "decode", "mbr", "bmuf"]
     table = dict(rnnt=golden_rnnt, frontend=golden_frontend, specaug=golden_specaug,
                  encoder=golden_encoder_eval, model=golden_model, decode=golden_decode, mbr=golden_mbr, bmuf=golden_bmuf,
-                 model_full=golden_model_full, decode_big=golden_decode_big, decode_fst=golden_decode_fst)
+                 model_full=golden_model_full, decode_big=golden_decode_big, decode_fst=golden_decode_fst, model_xf=golden_model_xf,
+                 decode_xf=golden_decode_xf)
     for w in which:
         table[w]()
