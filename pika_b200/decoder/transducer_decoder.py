@@ -142,9 +142,12 @@ class TransducerDecoder():
         # on-the-fly FST shallow fusion (decoder/beam_transducer.py:135-159,167-176): lm_scorer = pika_b200.decoder.sorted_matcher.SortedMatcher
         self.lm_scorer, self.lm_scorer_scale = lm_scorer, float(lm_scorer_scale)
         self.lm_max_states = 16
-        for name in ("las_rescorer", "las_rescorer_bw", "bilas_rescorer"):
-            if args is not None and getattr(args, name, None) is not None:
-                raise NotImplementedError("pika_b200: LAS rescoring is outside the hot path")
+        # LAS rescoring hooks (decoder/transducer_decoder.py:56-62, 219-253): the rescorer networks are the caller's own modules
+        # (decode_transducer.py:22-38 unpickles them); this class only scores a hypothesis with them, like the reference's
+        self.las_rescorer = getattr(args, "las_rescorer", None) if args is not None else None
+        self.las_rescorer_bw = getattr(args, "las_rescorer_bw", None) if args is not None else None
+        if args is not None and getattr(args, "bilas_rescorer", None) is not None:
+            self.bilas_rescorer = args.bilas_rescorer
         self.xf = model.decoder_type != "rnn"            # convolutional-transformer prediction net (decoder/transducer_decoder.py:117-120,151-171)
         if self.xf and lm_scorer is not None:
             raise NotImplementedError("pika_b200: FST fusion is wired to the LSTM prediction net only")
@@ -291,6 +294,33 @@ class TransducerDecoder():
                 break
         self.last_replays = 0
         return self._extract(ws, enc, B)
+
+    # ------------------------------------------------------------------------------------------------ LAS rescoring hooks
+    @staticmethod
+    def _token_log_probs(proj, tgt, scale=1.0):
+        """log_softmax(scale * proj) [T, 1, C] -> the log-probability of tgt[t + 1] at every step t (decoder/transducer_decoder.py:234-238)"""
+        assert proj.is_cuda, "pika_b200 scores on the GPU (there is no CPU fallback)"
+        logits = proj.squeeze(1).float().contiguous()
+        lp = torch.empty_like(logits)
+        K.log_softmax(logits, lp, logits.shape[1], scale)
+        tgt_idx = tgt[1:].squeeze(-1).squeeze(-1).to(lp.device)
+        return lp[torch.arange(tgt_idx.size(0), device=lp.device), tgt_idx].tolist()
+
+    @torch.no_grad()
+    def las_rescore(self, x, tgt, bw=False):
+        """x [T, 1, C] encoder outputs, tgt [L, 1, 1] = SOS + hypothesis + EOS -> per-token log-probs of the (backward) LAS rescorer
+        (decoder/transducer_decoder.py:219-238)"""
+        net = self.las_rescorer_bw if bw else self.las_rescorer
+        lens = torch.IntTensor([x.size(0)])
+        outputs, _, _, _ = net(x, tgt, lens)
+        return self._token_log_probs(net.dec_proj(outputs), tgt)
+
+    @torch.no_grad()
+    def bilas_rescore(self, x, tgt):
+        """bidirectional LAS rescorer, logits halved before the softmax (decoder/transducer_decoder.py:240-253)"""
+        lens, ali_lens = torch.IntTensor([x.size(0)]), torch.IntTensor([tgt.size(0)])
+        outputs, _, _, _ = self.bilas_rescorer(x, tgt, lens, None, True, True, ali_lens)
+        return self._token_log_probs(self.bilas_rescorer.dec_proj(outputs), tgt, 0.5)
 
     def _extract(self, ws, enc, B):
         step = int(ws.step_ctx[0].item())                                       # beam steps actually executed

@@ -43,7 +43,11 @@ class BmufTrainer():
             self.flat.data.copy_(self.param)
             engine.invalidate_weights()
         self.delta_prev = torch.zeros_like(self.param)
-        self.delta = torch.empty_like(self.param)
+        self.delta = torch.zeros_like(self.param)
+        if world_size > 1:
+            # the first all-reduce of a communicator sets up its channels / buffers for this message size (measured on 8 B200s: ~150 ms
+            # against 2.3 ms for every later block sync): pay that at construction, next to the parameter broadcast, not in the first block
+            dist.all_reduce(self.delta, op=dist.ReduceOp.SUM)
         self.health = torch.zeros(2, dtype=torch.float32, device=self.param.device)   # [absmax, unused]
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.param.device)
 

@@ -177,3 +177,35 @@ def test_decode_fst_shallow_fusion_matches_reference(golden_dir, name, beam, nbe
                 assert abs(sc - float(f["%s_score_%d_%d" % (name, b, n)])) < 1e-3 * abs(sc) + 1e-3
     finally:
         engine.set_precision("bf16")
+
+
+def test_las_rescoring_hooks_call_the_users_rescorer():
+    """decoder/transducer_decoder.py:219-253: the hooks run the caller's LAS module (any module with the reference's call signature and
+    a ``dec_proj``), take log_softmax of the projected outputs (halved logits for the bidirectional one) and pick tgt[1:]"""
+    import torch.nn.functional as F
+    from pika_b200.decoder.transducer_decoder import TransducerDecoder
+
+    class StubLas(torch.nn.Module):
+        def __init__(self, C, V, seed):
+            super().__init__()
+            torch.manual_seed(seed)
+            self.mix = torch.nn.Linear(C, 32)
+            self.dec_proj = torch.nn.Linear(32, V)
+
+        def forward(self, x, tgt, lens, *rest):
+            L = tgt.size(0)
+            ctx = self.mix(x).mean(0, keepdim=True).expand(L - 1, 1, -1)           # [L-1, 1, 32]: one output per predicted token
+            return ctx + 0.1 * torch.arange(L - 1, device=x.device).view(-1, 1, 1), None, None, None
+
+    C, V = 64, 50
+    a, b, c = StubLas(C, V, 1).cuda(), StubLas(C, V, 2).cuda(), StubLas(C, V, 3).cuda()
+    dargs = types.SimpleNamespace(las_rescorer=a, las_rescorer_bw=b, bilas_rescorer=c, nonblk_reward=0.0)
+    m = types.SimpleNamespace(decoder_type="rnn")
+    dec = TransducerDecoder(m, 1, 4, n_best=1, blk=0, global_scorer=None, cuda=True, args=dargs)
+    x = torch.randn(17, 1, C, device="cuda")
+    tgt = torch.tensor([0, 7, 3, 9, 1], device="cuda").view(-1, 1, 1)
+    for got, net, scale in ((dec.las_rescore(x, tgt), a, 1.0), (dec.las_rescore(x, tgt, bw=True), b, 1.0), (dec.bilas_rescore(x, tgt), c, 0.5)):
+        out = net(x, tgt, None)[0]
+        lp = F.log_softmax(scale * net.dec_proj(out), dim=-1).squeeze(1)
+        ref = lp[torch.arange(4), tgt[1:].view(-1)].tolist()
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
