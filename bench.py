@@ -133,8 +133,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-NCU_FC2_TRAFFIC_BYTES = 17.231e9       # dram__bytes_read.sum + dram__bytes_write.sum of one plain fc2 launch (profiles/r01_gemm_fc2.ncu.txt)
-NCU_FC2_LSE_TRAFFIC_BYTES = 18.768e9   # same for the launch with the row-LSE epilogue (profiles/r01_gemm_fc2_lse.ncu.txt)
+NCU_FC2_TRAFFIC_BYTES = 20.05e9        # dram__bytes_read.sum + dram__bytes_write.sum of one plain fc2 launch (profiles/r02_gemm_fc2_fwd.ncu.txt: 6.16 + 13.89 GB)
+NCU_FC2_LSE_TRAFFIC_BYTES = 18.836e9   # same for the launch with the row-LSE epilogue (profiles/r02_gemm_fc2_fwd_lse.ncu.txt: 4.52 + 14.31 GB)
 CPU_THREADS_CAP = 32      # first candidate thread count of the CPU arm; "all cores" is the second, the faster one is kept (measured per run)
 
 
@@ -534,9 +534,9 @@ def run_ours(a):
         "roofline": {"kernel": "gemm_tcgen05_kernel (joint fc2 forward, M=%d N=%d K=%d, bias%s)" % (R, a.V, H, " + fused row-LSE epilogue" if fused_lse else ""), "bound": "tensor",
                      "achieved": g_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": g_tf / tf_burst,
                      "traffic": (NCU_FC2_LSE_TRAFFIC_BYTES if fused_lse else NCU_FC2_TRAFFIC_BYTES) if (R, a.V, H) == (1159680, 6000, 1024) else None,
-                     "traffic_source": ("profiles/r01_gemm_fc2_lse.ncu.txt (dram read 4.67 GB + write 14.10 GB per launch" if fused_lse else
-                                        "profiles/r01_gemm_fc2.ncu.txt (dram read 3.36 GB + write 13.88 GB per launch") +
-                                       "; algorithmic: A 2.38 GB + B 0.012 GB + C 13.92 GB (+ 0.22 GB row partials when fused))",
+                     "traffic_source": ("profiles/r02_gemm_fc2_fwd_lse.ncu.txt (one `ncu --set full` capture of this kernel at this shape: dram read 4.52 GB + write 14.31 GB per launch" if fused_lse else
+                                        "profiles/r02_gemm_fc2_fwd.ncu.txt (one `ncu --set full` capture: dram read 6.16 GB + write 13.89 GB per launch") +
+                                       "; a committed constant, not measured in this run; algorithmic: A 2.38 GB + B 0.012 GB + C 13.92 GB (+ 0.45 GB row partials when fused))",
                      "launch_ms": g_ms, "launch_ms_plain_epilogue": g_ms_plain},
         "roofline_loss": {"kernel": ("rnnt_rowfinish + rnnt_lattice + rnnt_grad (first pass done in the fc2 GEMM epilogue)" if fused_lse else
                                      "rnnt_rowstats + rnnt_lattice + rnnt_grad (fused log-softmax + RNN-T loss + gradient)"), "bound": "hbm",

@@ -10,6 +10,12 @@ void count_launch();
 
 template <typename T> struct V8 {};   // 8 consecutive elements
 template <> struct V8<__nv_bfloat16> {
+    struct Raw { uint4 q; };                                    // the 16 bytes as loaded (kept packed while a prefetch is in flight)
+    PK_DEVICE static Raw load_raw(const __nv_bfloat16* p) { return Raw{*reinterpret_cast<const uint4*>(p)}; }
+    PK_DEVICE static void unpack(const Raw& r, float (&f)[8]) {
+        f[0] = bf16lo(r.q.x); f[1] = bf16hi(r.q.x); f[2] = bf16lo(r.q.y); f[3] = bf16hi(r.q.y);
+        f[4] = bf16lo(r.q.z); f[5] = bf16hi(r.q.z); f[6] = bf16lo(r.q.w); f[7] = bf16hi(r.q.w);
+    }
     PK_DEVICE static void load(const __nv_bfloat16* p, float (&f)[8]) {
         const uint4 q = *reinterpret_cast<const uint4*>(p);
         f[0] = bf16lo(q.x); f[1] = bf16hi(q.x); f[2] = bf16lo(q.y); f[3] = bf16hi(q.y);
@@ -21,6 +27,11 @@ template <> struct V8<__nv_bfloat16> {
     }
 };
 template <> struct V8<float> {
+    struct Raw { float4 a, b; };
+    PK_DEVICE static Raw load_raw(const float* p) { return Raw{*reinterpret_cast<const float4*>(p), *reinterpret_cast<const float4*>(p + 4)}; }
+    PK_DEVICE static void unpack(const Raw& r, float (&f)[8]) {
+        f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+    }
     PK_DEVICE static void load(const float* p, float (&f)[8]) {
         const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
         f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -672,6 +683,116 @@ __global__ void __launch_bounds__(128) joint_gate_bwd_py_kernel(const T* __restr
     }
 }
 
+// backward, BOTH reductions in one pass over dh: one CTA per (batch element, 32-channel slice), one WARP per 8 channels, the 32
+// lanes of a warp over the labels: a lane owns u = lane + 32 i (i < UI) of its warp's 8 channels for ALL frames, so its dpy sums stay
+// in registers for the whole kernel (the sum over t runs in one thread, in frame order, like the two-pass kernel), while the dex sums
+// of a frame are reduced over the lanes by a transposing butterfly (16 values over 32 lanes in 16 shuffles).  Warps never meet after
+// the prologue.  dh is read once (the two-pass form read it twice) and every tanh / sigmoid is evaluated once instead of twice.
+template <typename T, int UI>
+__global__ void __launch_bounds__(128) joint_gate_bwd_fused_kernel(const T* __restrict__ ex, const T* __restrict__ py, const T* __restrict__ dh,
+                                                                   T* __restrict__ dex, T* __restrict__ dpy, int B, int Tt, int U1, int H) {
+    extern __shared__ __align__(16) uint8_t jg_smem[];
+    T* s_py = reinterpret_cast<T*>(jg_smem);                   // [2 parts][4 channel groups][U1][8]: conflict-free 16-byte rows per lane
+    const int slices = H / 32;
+    const int b = blockIdx.x / slices, cs = blockIdx.x - b * slices;
+    const int tid = threadIdx.x, ct = tid >> 5, lane = tid & 31;
+    const int c0 = cs * 32 + ct * 8;
+    for (int i = tid; i < U1 * 8; i += 128) {
+        const int u = i >> 3, v = i & 7;                       // v < 4: fc1 part, else gate part; v & 3 = channel group
+        float f[8];
+        V8<T>::load(py + ((long long)b * U1 + u) * 2 * H + (v >> 2) * H + cs * 32 + (v & 3) * 8, f);
+        V8<T>::store(s_py + ((long long)(v * U1) + u) * 8, f);
+    }
+    float a1u[UI][8], agu[UI][8];
+#pragma unroll
+    for (int i = 0; i < UI; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a1u[i][e] = 0.f; agu[i][e] = 0.f; }
+    __syncthreads();
+    const T* s_p1 = s_py + (long long)(ct * U1) * 8;
+    const T* s_pg = s_py + (long long)((4 + ct) * U1) * 8;
+    const T* dh_b = dh + (long long)b * Tt * U1 * H + c0;
+    const T* ex_b = ex + (long long)b * Tt * 2 * H + c0;
+    typename V8<T>::Raw dn[UI], e1n, egn;                      // next frame's operands, fetched one frame ahead (kept packed)
+#pragma unroll
+    for (int i = 0; i < UI; ++i) {
+        const int u = lane + 32 * i;
+        if (u < U1) dn[i] = V8<T>::load_raw(dh_b + (long long)u * H);
+    }
+    e1n = V8<T>::load_raw(ex_b);
+    egn = V8<T>::load_raw(ex_b + H);
+    for (int t = 0; t < Tt; ++t) {
+        float e1[8], eg[8];
+        typename V8<T>::Raw dc[UI];
+        V8<T>::unpack(e1n, e1);
+        V8<T>::unpack(egn, eg);
+#pragma unroll
+        for (int i = 0; i < UI; ++i) dc[i] = dn[i];
+        if (t + 1 < Tt) {
+#pragma unroll
+            for (int i = 0; i < UI; ++i) {
+                const int u = lane + 32 * i;
+                if (u < U1) dn[i] = V8<T>::load_raw(dh_b + ((long long)(t + 1) * U1 + u) * H);
+            }
+            e1n = V8<T>::load_raw(ex_b + (long long)(t + 1) * 2 * H);
+            egn = V8<T>::load_raw(ex_b + (long long)(t + 1) * 2 * H + H);
+        }
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = 0.f;
+#pragma unroll
+        for (int i = 0; i < UI; ++i) {
+            const int u = lane + 32 * i;
+            if (u < U1) {
+                float p1[8], pg[8], d[8];
+                V8<T>::unpack(dc[i], d);
+                V8<T>::load(s_p1 + u * 8, p1);
+                V8<T>::load(s_pg + u * 8, pg);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float a = jt_tanh<T>(e1[e] + p1[e]), g = jt_sigmoid<T>(eg[e] + pg[e]);
+                    const float dg = d[e] * g;
+                    const float t1 = dg * (1.f - a * a), tg = dg * a * (1.f - g);
+                    a1u[i][e] += t1; agu[i][e] += tg;
+                    v[e] += t1; v[8 + e] += tg;
+                }
+            }
+        }
+        // 16 sums x 32 lanes -> lane l ends with sum number (l >> 1)
+        float w8[8], w4[4], w2[2];
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float keep = h16 ? v[i + 8] : v[i], send = h16 ? v[i] : v[i + 8];
+            w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float keep = h8 ? w8[i + 4] : w8[i], send = h8 ? w8[i] : w8[i + 4];
+            w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float keep = h4 ? w4[i + 2] : w4[i], send = h4 ? w4[i] : w4[i + 2];
+            w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        float w1 = (h2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? w2[0] : w2[1], 2);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+        if ((lane & 1) == 0) {
+            const int j = lane >> 1;                           // = 8*h16 + 4*h8 + 2*h4 + h2: fc1 sums 0..7, gate sums 8..15
+            dex[((long long)b * Tt + t) * 2 * H + (j >> 3) * H + c0 + (j & 7)] = from_f32<T>(w1);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < UI; ++i) {
+        const int u = lane + 32 * i;
+        if (u < U1) {
+            V8<T>::store(dpy + ((long long)b * U1 + u) * 2 * H + c0, a1u[i]);
+            V8<T>::store(dpy + ((long long)b * U1 + u) * 2 * H + H + c0, agu[i]);
+        }
+    }
+}
+
 // =============================================================================== LSTM cell (gate order i,f,g,o)
 // gates = gx[b, :4H] + gh[b, :4H] (f32 both: gx holds W_ih x + b_ih + b_hh for this step)
 template <typename T>
@@ -981,9 +1102,23 @@ extern "C" int pk_joint_gate_fwd(const void* ex, const void* py, void* h, int dt
     PK_DISPATCH_T(dtype, (joint_gate_fwd_kernel<T><<<B * T_, 128, 0, STREAM(stream)>>>((const T*)ex, (const T*)py, (T*)h, B, T_, U1, H, ld_h)));
     DONE();
 }
+template <typename T, int UI>
+static void launch_gate_bwd_fused(const void* ex, const void* py, const void* dh, void* dex, void* dpy, int B, int T_, int U1, int H, cudaStream_t st) {
+    const int smem = U1 * 64 * (int)sizeof(T);
+    joint_gate_bwd_fused_kernel<T, UI><<<B * (H / 32), 128, smem, st>>>((const T*)ex, (const T*)py, (const T*)dh, (T*)dex, (T*)dpy, B, T_, U1, H);
+}
 extern "C" int pk_joint_gate_bwd(const void* ex, const void* py, const void* dh, void* dex, void* dpy, int dtype, int B, int T_, int U1,
                                  int H, void* stream) {
     PK_CHECK_ARG(H % 8 == 0, "H must be a multiple of 8");
+    static const bool two_pass = getenv("PK_GATE_BWD_TWO_PASS") && atoi(getenv("PK_GATE_BWD_TWO_PASS")) != 0;      // A/B switch
+    const int ui = (U1 + 31) / 32;
+    if (!two_pass && H % 32 == 0 && ui <= 5) {
+        cudaStream_t st = STREAM(stream);
+#define PK_GATE_CASE(N) case N: { PK_DISPATCH_T(dtype, (launch_gate_bwd_fused<T, N>(ex, py, dh, dex, dpy, B, T_, U1, H, st))); } break;
+        switch (ui) { PK_GATE_CASE(1) PK_GATE_CASE(2) PK_GATE_CASE(3) PK_GATE_CASE(4) PK_GATE_CASE(5) }
+#undef PK_GATE_CASE
+        DONE();
+    }
     PK_DISPATCH_T(dtype, (joint_gate_bwd_ex_kernel<T><<<B * T_, 128, 0, STREAM(stream)>>>((const T*)ex, (const T*)py, (const T*)dh, (T*)dex, B, T_, U1, H)));
     PK_CHECK_LAUNCH(); count_launch();
     PK_DISPATCH_T(dtype, (joint_gate_bwd_py_kernel<T><<<B * U1, 128, 0, STREAM(stream)>>>((const T*)ex, (const T*)py, (const T*)dh, (T*)dpy, B, T_, U1, H)));

@@ -45,16 +45,52 @@ PK_DEVICE void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// same copy delivered to the same shared-memory offset (and signalled on the mbarrier at the same offset) of every CTA in ``mask``
+PK_DEVICE void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+PK_DEVICE uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 PK_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-PK_DEVICE void grid_barrier(unsigned int* counter, unsigned int target) {
+// mode 0: membar.gl + relaxed atomic + volatile polling + membar.gl (round 1).  mode 1 (default): release reduction, acquire polling loads
+// (this CTA's writes of the step are ordered before its arrival by bar.sync + cumulativity; no separate membar.gl on either side).
+// mode 3: hierarchical (measured SLOWER than mode 1: 6.49 vs 5.81 us per forward step, two cluster barriers cost more than the contention
+// they remove) -- the hardware cluster barrier gathers the cn CTAs of a cluster, ONE
+// thread per cluster does the mode-1 handshake on the global counter (128 -> 16 serialised atomics on one line), a second cluster
+// barrier releases the peers.  Causality chains through the cluster-scope and gpu-scope release/acquire pairs.  PK_LSTM_BARRIER selects.
+PK_DEVICE void grid_barrier(unsigned int* counter, unsigned int step_index, int mode, uint32_t cn, uint32_t cr) {
+    if (mode == 3 && cn > 1) {
+        cluster_sync_all();
+        if (cr == 0 && threadIdx.x == 0) {
+            const unsigned int target = (gridDim.x / cn) * step_index;
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            } while (seen < target);
+        }
+        cluster_sync_all();
+        return;
+    }
+    const unsigned int target = gridDim.x * step_index;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+        if (mode == 0) {
+            __threadfence();
+            atomicAdd(counter, 1u);
+            while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+            }
+            __threadfence();
+        } else {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            } while (seen < target);
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -66,7 +102,7 @@ PK_DEVICE float sigm(float x) { return 1.f / (1.f + __expf(-x)); }
 template <typename T>
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ w_hh,
                                                                      T* __restrict__ out, __nv_bfloat16* hx, float* __restrict__ gates_save,
-                                                                     float* __restrict__ cs, int B, int Bt, int U, int H, unsigned int* counter) {
+                                                                     float* __restrict__ cs, int B, int Bt, int U, int H, unsigned int* counter, int bar_mode) {
     // B = sequences of this launch (<= 32); Bt = sequences of the whole batch: gates_save / cs are time-major [U, Bt, .] and the
     // caller passes them already offset to this launch's first sequence (batches larger than 32 run as independent launches)
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -89,7 +125,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float
     __shared__ __align__(8) uint64_t h_bar;
     if (tid == 0) { mbar_init(&h_bar, 1); mbar_fence_init(); }
     uint32_t h_phase = 0;
+    const uint32_t cn = cluster_nctarank(), cr = cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << cn) - 1u);
     __syncthreads();
+    if (cn > 1) cluster_sync_all();                                              // every peer's barrier exists before the first multicast
     for (int t = 0; t < U; ++t) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         // this step's input-projection terms do not depend on h_{t-1}: fetch them now so that their L2 / HBM latency hides behind the
@@ -102,24 +141,37 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float
         if (t > 0) {
             // all-gather of h_{t-1} (32 x H bf16) from L2 by the TMA engine: lane r of warp 0 copies row r
             const __nv_bfloat16* src = hx + (long long)((t - 1) & 1) * LS_MB * H;
+            // the CTAs of a cluster share the gather: each fetches 32 / cn of the rows and multicasts them to all cn (one L2 read per
+            // cluster instead of one per CTA -- with 128 CTAs pulling the same 64 KB every step the L2 was the bottleneck)
             if (warp == 0) {
                 fence_proxy_async_all();
                 if (lane == 0) mbar_arrive_expect_tx(&h_bar, 32u * (uint32_t)H * 2u);
                 __syncwarp();
-                bulk_g2s(h_s + lane * P, src + (long long)lane * H, (uint32_t)H * 2u, &h_bar);
+                if (cn == 1) bulk_g2s(h_s + lane * P, src + (long long)lane * H, (uint32_t)H * 2u, &h_bar);
+                else if ((lane % cn) == cr) bulk_g2s_mc(h_s + lane * P, src + (long long)lane * H, (uint32_t)H * 2u, &h_bar, cmask);
             }
             mbar_wait(&h_bar, h_phase);
             h_phase ^= 1;
             const __nv_bfloat16* ar0 = h_s + (mt * 16 + g) * P + 2 * tq;
             const __nv_bfloat16* ar1 = ar0 + 8 * P;
             const __nv_bfloat16* br = w_s + (nt * 8 + g) * P + 2 * tq;
-#pragma unroll 8
-            for (int k0 = 0; k0 < H; k0 += 16) {
+            // four independent accumulator chains: one chain would serialise H/16 = 64 dependent tensor-core instructions per step
+            float acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f}, acc3[4] = {0.f, 0.f, 0.f, 0.f};
+            auto mma_at = [&](float (&c)[4], int k0) {
                 const uint32_t a0 = *reinterpret_cast<const uint32_t*>(ar0 + k0), a1 = *reinterpret_cast<const uint32_t*>(ar1 + k0);
                 const uint32_t a2 = *reinterpret_cast<const uint32_t*>(ar0 + k0 + 8), a3 = *reinterpret_cast<const uint32_t*>(ar1 + k0 + 8);
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(br + k0), b1 = *reinterpret_cast<const uint32_t*>(br + k0 + 8);
-                mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
+                mma_bf16_16816(c, a0, a1, a2, a3, b0, b1);
+            };
+#pragma unroll 4
+            for (int k0 = 0; k0 < H; k0 += 64) {
+                mma_at(acc, k0);
+                mma_at(acc1, k0 + 16);
+                mma_at(acc2, k0 + 32);
+                mma_at(acc3, k0 + 48);
             }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = (acc[e] + acc1[e]) + (acc2[e] + acc3[e]);
         }
         g_s[(mt * 16 + g) * 33 + nt * 8 + 2 * tq] = acc[0];
         g_s[(mt * 16 + g) * 33 + nt * 8 + 2 * tq + 1] = acc[1];
@@ -142,7 +194,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float
         } else {
             hx[(long long)(t & 1) * LS_MB * H + (long long)cb * H + j0 + cj] = __float2bfloat16_rn(0.f);
         }
-        if (t + 1 < U) grid_barrier(counter, (unsigned int)(gridDim.x * (t + 1)));
+        if (t + 1 < U) grid_barrier(counter, (unsigned int)(t + 1), bar_mode, cn, cr);
     }
 }
 
@@ -152,7 +204,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const float
 template <typename T>
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __restrict__ dout, const float* __restrict__ gates_save,
                                                                      const float* __restrict__ cs, const __nv_bfloat16* __restrict__ w_hh,
-                                                                     __nv_bfloat16* dG, int B, int Bt, int U, int H, unsigned int* counter) {
+                                                                     __nv_bfloat16* dG, int B, int Bt, int U, int H, unsigned int* counter, int bar_mode) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     const int G4 = 4 * H;
     const int PW = G4 + LS_PAD;                                                  // Wt_s pitch
@@ -175,7 +227,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
     const int mt = warp & 1, kg = warp >> 1;                                     // 2 m-tiles x 4 K-groups
     const int g = lane >> 2, tq = lane & 3;
     uint32_t q_phase[2] = {0, 0};
+    const uint32_t cn = cluster_nctarank(), cr = cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << cn) - 1u);
     __syncthreads();
+    if (cn > 1) cluster_sync_all();                                              // every peer's barriers exist before the first multicast
     for (int t = U - 1; t >= 0; --t) {
         for (int i = tid; i < 32 * 9; i += LS_THREADS) r_s[i] = 0.f;
         // saved forward values of this step: independent of the recurrent gradient, fetched before the product (latency off the critical path)
@@ -195,12 +250,19 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
                     fence_proxy_async_all();
                     if (lane == 0) mbar_arrive_expect_tx(&q_bar[qtr & 1], (uint32_t)B * (uint32_t)KQ * 2u);
                     __syncwarp();
-                    if (lane < B) bulk_g2s(d_s + ((qtr & 1) * 32 + lane) * PD, src + (long long)lane * G4 + qtr * KQ, (uint32_t)KQ * 2u, &q_bar[qtr & 1]);
+                    __nv_bfloat16* dst = d_s + ((qtr & 1) * 32 + lane) * PD;
+                    const __nv_bfloat16* from = src + (long long)lane * G4 + qtr * KQ;
+                    if (lane < B) {
+                        // cluster: each CTA fetches every cn-th row and multicasts it to all cn CTAs (every CTA needs the whole 256 KB
+                        // row block each step: one L2 read per cluster instead of one per CTA)
+                        if (cn == 1) bulk_g2s(dst, from, (uint32_t)KQ * 2u, &q_bar[qtr & 1]);
+                        else if ((lane % cn) == cr) bulk_g2s_mc(dst, from, (uint32_t)KQ * 2u, &q_bar[qtr & 1], cmask);
+                    }
                 }
             };
             issue(0);
             issue(1);
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f}, accc[4] = {0.f, 0.f, 0.f, 0.f}, accd[4] = {0.f, 0.f, 0.f, 0.f};
             const int kspan = KQ / 4;                                            // per K-group
             for (int qtr = 0; qtr < 4; ++qtr) {
                 mbar_wait(&q_bar[qtr & 1], q_phase[qtr & 1]);
@@ -208,18 +270,29 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
                 const __nv_bfloat16* ar0 = d_s + ((qtr & 1) * 32 + mt * 16 + g) * PD + kg * kspan + 2 * tq;
                 const __nv_bfloat16* ar1 = ar0 + 8 * PD;
                 const __nv_bfloat16* br = wt_s + g * PW + qtr * KQ + kg * kspan + 2 * tq;
-#pragma unroll 8
-                for (int k0 = 0; k0 < kspan; k0 += 16) {
+                auto mma_at = [&](float (&c)[4], int k0) {
                     const uint32_t a0 = *reinterpret_cast<const uint32_t*>(ar0 + k0), a1 = *reinterpret_cast<const uint32_t*>(ar1 + k0);
                     const uint32_t a2 = *reinterpret_cast<const uint32_t*>(ar0 + k0 + 8), a3 = *reinterpret_cast<const uint32_t*>(ar1 + k0 + 8);
                     const uint32_t b0 = *reinterpret_cast<const uint32_t*>(br + k0), b1 = *reinterpret_cast<const uint32_t*>(br + k0 + 8);
-                    mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
+                    mma_bf16_16816(c, a0, a1, a2, a3, b0, b1);
+                };
+                int k0 = 0;
+#pragma unroll 4
+                for (; k0 + 64 <= kspan; k0 += 64) {
+                    mma_at(acc, k0);
+                    mma_at(accb, k0 + 16);
+                    mma_at(accc, k0 + 32);
+                    mma_at(accd, k0 + 48);
                 }
+                for (; k0 < kspan; k0 += 16) mma_at(acc, k0);                    // kspan = H / 4 is a multiple of 16, not always of 64
                 if (qtr + 2 < 4) {
-                    __syncthreads();                                             // every warp is done reading this buffer
+                    if (cn == 1) __syncthreads();                                // every warp is done reading this buffer
+                    else cluster_sync_all();                                     // ... in every CTA of the cluster: peers write into it too
                     issue(qtr + 2);
                 }
             }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = (acc[e] + accb[e]) + (accc[e] + accd[e]);     // four independent tensor-core chains
             atomicAdd(&r_s[(mt * 16 + g) * 9 + 2 * tq], acc[0]);
             atomicAdd(&r_s[(mt * 16 + g) * 9 + 2 * tq + 1], acc[1]);
             atomicAdd(&r_s[(mt * 16 + g + 8) * 9 + 2 * tq], acc[2]);
@@ -239,13 +312,41 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const T* __
             d[3 * H] = __float2bfloat16_rn(dh * tc * go * (1.f - go));
             dc_state = dc * gf;
         }
-        if (t > 0) grid_barrier(counter, (unsigned int)(gridDim.x * (U - t)));
+        if (t > 0) grid_barrier(counter, (unsigned int)(U - t), bar_mode, cn, cr);
     }
 }
 }  // namespace pk
 
 using namespace pk;
 
+static int lstm_bar_mode() {
+    static const int m = getenv("PK_LSTM_BARRIER") ? atoi(getenv("PK_LSTM_BARRIER")) : 1;
+    return m;
+}
+// cooperative launch with thread-block clusters of ``cs`` CTAs; cs is the largest of 8/4/2 for which the whole grid is co-resident
+static int lstm_launch(const void* fn, int grid, int smem, void** args, cudaStream_t st, int* cluster_cache) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    if (*cluster_cache == 0) {
+        static const int want = getenv("PK_LSTM_CLUSTER") ? atoi(getenv("PK_LSTM_CLUSTER")) : 8;
+        int pick = 1;
+        for (int cs = want; cs >= 2; cs >>= 1) {
+            if (grid % cs) continue;
+            attr[1].id = cudaLaunchAttributeClusterDimension; attr[1].val.clusterDim.x = cs; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 2;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) == cudaSuccess && ncl * cs >= grid) { pick = cs; break; }
+            (void)cudaGetLastError();
+        }
+        *cluster_cache = pick;
+    }
+    attr[1].id = cudaLaunchAttributeClusterDimension; attr[1].val.clusterDim.x = *cluster_cache; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    PK_CHECK_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    return 0;
+}
 static int lstm_seq_check(int B, int U, int H) {
     PK_CHECK_ARG(B >= 1, "empty batch");
     PK_CHECK_ARG(U >= 1 && H % 64 == 0 && H / LS_HJ <= num_sms(), "H must be a multiple of 64 with H/8 <= #SMs");
@@ -266,6 +367,7 @@ extern "C" int pk_lstm_seq_fwd(const float* gx, const void* w_hh_bf16, void* out
     const void* fn = out_dtype == PK_BF16 ? (const void*)lstm_seq_fwd_kernel<__nv_bfloat16> : (const void*)lstm_seq_fwd_kernel<float>;
     PK_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const size_t es = out_dtype == PK_BF16 ? 2 : 4;
+    int bar_mode = lstm_bar_mode();
     for (int b0 = 0; b0 < B; b0 += LS_MB) {                    // sequences are independent: 32 per cooperative launch
         int nb = B - b0 < LS_MB ? B - b0 : LS_MB, Bt = B;
         const float* gx_c = gx + (long long)b0 * U * 4 * H;
@@ -274,8 +376,13 @@ extern "C" int pk_lstm_seq_fwd(const float* gx, const void* w_hh_bf16, void* out
         float* cs_c = cs + (long long)b0 * H;
         PK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
         void* args[] = {(void*)&gx_c, (void*)&w, (void*)&out_c, (void*)&hx, (void*)&gs_c, (void*)&cs_c, (void*)&nb, (void*)&Bt, (void*)&U, (void*)&H,
-                        (void*)&counter};
-        PK_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(H / LS_HJ), dim3(LS_THREADS), args, smem, st));
+                        (void*)&counter, (void*)&bar_mode};
+        static int cluster_f[2] = {0, 0};                      // per kernel flavour (the cluster choice depends on the grid = H / 8 too:
+        static int grid_f[2] = {0, 0};                         //  re-evaluated when H changes)
+        const int fl = out_dtype == PK_BF16 ? 0 : 1;
+        if (grid_f[fl] != H / LS_HJ) { grid_f[fl] = H / LS_HJ; cluster_f[fl] = 0; }
+        rc = lstm_launch(fn, H / LS_HJ, smem, args, st, &cluster_f[fl]);
+        if (rc) return rc;
         count_launch();
     }
     return 0;
@@ -292,6 +399,7 @@ extern "C" int pk_lstm_seq_bwd(const void* dout, int dtype, const float* gates_s
     const void* fn = dtype == PK_BF16 ? (const void*)lstm_seq_bwd_kernel<__nv_bfloat16> : (const void*)lstm_seq_bwd_kernel<float>;
     PK_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const size_t es = dtype == PK_BF16 ? 2 : 4;
+    int bar_mode = lstm_bar_mode();
     for (int b0 = 0; b0 < B; b0 += LS_MB) {
         int nb = B - b0 < LS_MB ? B - b0 : LS_MB, Bt = B;
         const void* dout_c = reinterpret_cast<const unsigned char*>(dout) + (size_t)b0 * U * H * es;
@@ -299,8 +407,13 @@ extern "C" int pk_lstm_seq_bwd(const void* dout, int dtype, const float* gates_s
         const float* cs_c = cs + (long long)b0 * H;
         __nv_bfloat16* dg = reinterpret_cast<__nv_bfloat16*>(dG_bf16) + (long long)b0 * G4;
         PK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
-        void* args[] = {(void*)&dout_c, (void*)&gs_c, (void*)&cs_c, (void*)&w, (void*)&dg, (void*)&nb, (void*)&Bt, (void*)&U, (void*)&H, (void*)&counter};
-        PK_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(H / LS_HJ), dim3(LS_THREADS), args, smem, st));
+        void* args[] = {(void*)&dout_c, (void*)&gs_c, (void*)&cs_c, (void*)&w, (void*)&dg, (void*)&nb, (void*)&Bt, (void*)&U, (void*)&H, (void*)&counter, (void*)&bar_mode};
+        static int cluster_b[2] = {0, 0};
+        static int grid_b[2] = {0, 0};
+        const int fl = dtype == PK_BF16 ? 0 : 1;
+        if (grid_b[fl] != H / LS_HJ) { grid_b[fl] = H / LS_HJ; cluster_b[fl] = 0; }
+        rc = lstm_launch(fn, H / LS_HJ, smem, args, st, &cluster_b[fl]);
+        if (rc) return rc;
         count_launch();
     }
     return 0;

@@ -72,6 +72,8 @@ bf, f32 = torch.bfloat16, torch.float32
 if which in ("fc2", "all", "fwd"):
     run("fc2_fwd_plain", R, 6000, 1024, False, False, bf, bias=True)
     run("fc2_fwd_lse", R, 6000, 1024, False, False, bf, lse=True, bias=True)
+if which == "lse":
+    run("fc2_fwd_lse", R, 6000, 1024, False, False, bf, lse=True, bias=True)
 if which in ("fc2", "all", "dgrad"):
     run("fc2_dgrad", R, 1024, 6000, False, True, bf)
 if which in ("fc2", "all", "wgrad"):
