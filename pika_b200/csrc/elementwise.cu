@@ -626,6 +626,62 @@ __global__ void __launch_bounds__(128) joint_gate_fwd_kernel(const T* __restrict
         }
     }
 }
+// forward, channel-sliced form: one CTA per (batch element, 32-channel slice) keeps its slice of py (all labels) in shared memory and
+// walks the frames, so py is read from L2 once per slice instead of once per (b, t) CTA (the frame-major kernel above re-reads the
+// whole [U1, 2H] block of its utterance for every frame: 4.7 GB of L2 reads at the config-2 shape, more than the 2.4 GB it writes).
+// Lanes: 4 channel groups x 8 labels per warp (a warp's store covers 64 contiguous bytes of 8 rows), 4 warps = 32 labels per pass.
+template <typename T, int UI>
+__global__ void __launch_bounds__(128) joint_gate_fwd_sliced_kernel(const T* __restrict__ ex, const T* __restrict__ py, T* __restrict__ h,
+                                                                    int B, int Tt, int U1, int H, int ld_h) {
+    extern __shared__ __align__(16) uint8_t jg_smem[];
+    T* s_py = reinterpret_cast<T*>(jg_smem);                   // [2 parts][4 channel groups][U1][8]
+    const int slices = H / 32;
+    const int b = blockIdx.x / slices, cs = blockIdx.x - b * slices;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ct = lane & 3, ul = (lane >> 2) + 8 * warp;
+    const int c0 = cs * 32 + ct * 8;
+    for (int i = tid; i < U1 * 8; i += 128) {
+        const int u = i >> 3, v = i & 7;
+        float f[8];
+        V8<T>::load(py + ((long long)b * U1 + u) * 2 * H + (v >> 2) * H + cs * 32 + (v & 3) * 8, f);
+        V8<T>::store(s_py + ((long long)(v * U1) + u) * 8, f);
+    }
+    __syncthreads();
+    const T* s_p1 = s_py + (long long)(ct * U1) * 8;
+    const T* s_pg = s_py + (long long)((4 + ct) * U1) * 8;
+    const T* ex_b = ex + (long long)b * Tt * 2 * H + c0;
+    typename V8<T>::Raw e1n = V8<T>::load_raw(ex_b), egn = V8<T>::load_raw(ex_b + H);
+    for (int t = 0; t < Tt; ++t) {
+        float e1[8], eg[8];
+        V8<T>::unpack(e1n, e1);
+        V8<T>::unpack(egn, eg);
+        if (t + 1 < Tt) {
+            e1n = V8<T>::load_raw(ex_b + (long long)(t + 1) * 2 * H);
+            egn = V8<T>::load_raw(ex_b + (long long)(t + 1) * 2 * H + H);
+        }
+        T* hrow = h + ((long long)(b * Tt + t) * U1) * ld_h + c0;
+#pragma unroll
+        for (int i = 0; i < UI; ++i) {
+            const int u = ul + 32 * i;
+            if (u < U1) {
+                float p1[8], pg[8], o[8];
+                V8<T>::load(s_p1 + u * 8, p1);
+                V8<T>::load(s_pg + u * 8, pg);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = jt_tanh<T>(e1[e] + p1[e]) * jt_sigmoid<T>(eg[e] + pg[e]);
+                V8<T>::store(hrow + (long long)u * ld_h, o);
+            }
+        }
+        if (ld_h > H && cs == 0 && ct == 0) {                   // the ones column of the fc2 bias gradient (see the frame-major kernel)
+            const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < UI; ++i) {
+                const int u = ul + 32 * i;
+                if (u < U1) V8<T>::store(h + ((long long)(b * Tt + t) * U1 + u) * ld_h + H, one);
+            }
+        }
+    }
+}
 // backward, reduction over u:  dex[b,t,:] = sum_u (d1, dg);    d1 = dh*g*(1-a^2), dg = dh*a*g*(1-g)
 template <typename T>
 __global__ void __launch_bounds__(128) joint_gate_bwd_ex_kernel(const T* __restrict__ ex, const T* __restrict__ py,
@@ -1097,14 +1153,29 @@ extern "C" int pk_log_softmax(const void* x, int dtype, long long ld, float* y, 
     DONE();
 }
 
+template <typename T, int UI>
+static void launch_gate_fwd_sliced(const void* ex, const void* py, void* h, int B, int T_, int U1, int H, int ld_h, cudaStream_t st) {
+    joint_gate_fwd_sliced_kernel<T, UI><<<B * (H / 32), 128, U1 * 64 * (int)sizeof(T), st>>>((const T*)ex, (const T*)py, (T*)h, B, T_, U1, H, ld_h);
+}
 extern "C" int pk_joint_gate_fwd(const void* ex, const void* py, void* h, int dtype, int B, int T_, int U1, int H, int ld_h, void* stream) {
-    PK_CHECK_ARG(H % 8 == 0 && (ld_h == H || ld_h == H + 8), "H % 8 == 0 and ld_h in {H, H+8}");
+    PK_CHECK_ARG(H % 8 == 0 && ld_h % 8 == 0 && ld_h >= H, "H, ld_h must be multiples of 8");
+    static const bool frame_major = getenv("PK_GATE_FWD_FRAME_MAJOR") && atoi(getenv("PK_GATE_FWD_FRAME_MAJOR")) != 0;      // A/B switch
+    const int ui = (U1 + 31) / 32;
+    if (!frame_major && H % 32 == 0 && ui <= 5 && T_ >= 8) {
+        cudaStream_t st = STREAM(stream);
+#define PK_GATE_CASE(N) case N: { PK_DISPATCH_T(dtype, (launch_gate_fwd_sliced<T, N>(ex, py, h, B, T_, U1, H, ld_h, st))); } break;
+        switch (ui) { PK_GATE_CASE(1) PK_GATE_CASE(2) PK_GATE_CASE(3) PK_GATE_CASE(4) PK_GATE_CASE(5) }
+#undef PK_GATE_CASE
+        DONE();
+    }
     PK_DISPATCH_T(dtype, (joint_gate_fwd_kernel<T><<<B * T_, 128, 0, STREAM(stream)>>>((const T*)ex, (const T*)py, (T*)h, B, T_, U1, H, ld_h)));
     DONE();
 }
+
 template <typename T, int UI>
 static void launch_gate_bwd_fused(const void* ex, const void* py, const void* dh, void* dex, void* dpy, int B, int T_, int U1, int H, cudaStream_t st) {
     const int smem = U1 * 64 * (int)sizeof(T);
+    // (capping the registers for 3 CTAs per SM instead of 2 -- 168 registers, 84 spilled bytes at UI = 5 -- measured slower: 1.77 vs 1.40 ms)
     joint_gate_bwd_fused_kernel<T, UI><<<B * (H / 32), 128, smem, st>>>((const T*)ex, (const T*)py, (const T*)dh, (T*)dex, (T*)dpy, B, T_, U1, H);
 }
 extern "C" int pk_joint_gate_bwd(const void* ex, const void* py, const void* dh, void* dex, void* dpy, int dtype, int B, int T_, int U1,
