@@ -287,33 +287,52 @@ template <typename T>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long rows, int C,
                                                      const float* __restrict__ w, const float* __restrict__ b, float eps,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    // one warp per row; C <= 1024: the row lives in registers (lane l owns columns [l*8 + k*256, +8)), x is read exactly once and the
+    // next row of the warp is already in flight (packed) while this one is reduced and written
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    typename V8<T>::Raw nx[4];
+    if (warp < rows) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int c = lane * 8 + k * 256; if (c < C) nx[k] = V8<T>::load_raw(x + warp * C + c); }
+    }
+    const float invC = 1.f / C;
     for (long long r = warp; r < rows; r += nw) {
-        const T* xr = x + r * C;
+        float f[4][8];
         float s = 0.f;
-        for (int c = lane * 8; c < C; c += 256) {
-            float f[8];
-            V8<T>::load(xr + c, f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s += f[e];
+        for (int k = 0; k < 4; ++k) {
+            const int c = lane * 8 + k * 256;
+            if (c < C) {
+                V8<T>::unpack(nx[k], f[k]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s += f[k][e];
+            }
         }
-        const float mu = warp_sum(s) / C;
+        if (r + nw < rows) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int c = lane * 8 + k * 256; if (c < C) nx[k] = V8<T>::load_raw(x + (r + nw) * C + c); }
+        }
+        const float mu = warp_sum(s) * invC;
         float v = 0.f;
-        for (int c = lane * 8; c < C; c += 256) {
-            float f[8];
-            V8<T>::load(xr + c, f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v += (f[e] - mu) * (f[e] - mu);
+        for (int k = 0; k < 4; ++k) {
+            const int c = lane * 8 + k * 256;
+            if (c < C) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v += (f[k][e] - mu) * (f[k][e] - mu);
+            }
         }
-        const float rs = rsqrtf(warp_sum(v) / C + eps);
-        for (int c = lane * 8; c < C; c += 256) {
-            float f[8];
-            V8<T>::load(xr + c, f);
+        const float rs = rsqrtf(warp_sum(v) * invC + eps);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = (f[e] - mu) * rs * w[c + e] + b[c + e];
-            V8<T>::store(y + r * C + c, f);
+        for (int k = 0; k < 4; ++k) {
+            const int c = lane * 8 + k * 256;
+            if (c < C) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[k][e] = (f[k][e] - mu) * rs * __ldg(w + c + e) + __ldg(b + c + e);   // L1-resident
+                V8<T>::store(y + r * C + c, f[k]);
+            }
         }
         if (lane == 0 && mean_out) { mean_out[r] = mu; rstd_out[r] = rs; }
     }
@@ -340,6 +359,21 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int e = 0; e < 8; ++e) { aw[k][e] = 0.f; ab[k][e] = 0.f; }
+    float wr[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = lane * 8 + k * 256;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) wr[k][e] = c < C ? w[c + e] : 0.f;
+    }
+    typename V8<T>::Raw ng[4], nf[4];                           // the warp's next row, in flight (packed) while this one is processed
+    if (warp < rows) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = lane * 8 + k * 256;
+            if (c < C) { ng[k] = V8<T>::load_raw(dy + warp * C + c); nf[k] = V8<T>::load_raw(x + warp * C + c); }
+        }
+    }
     for (long long r = warp; r < rows; r += nw) {
         const float mu = mean[r], rs = rstd[r];
         float s1 = 0.f, s2 = 0.f;
@@ -347,13 +381,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = lane * 8 + k * 256;
+            if (c < C) { V8<T>::unpack(ng[k], g[k]); V8<T>::unpack(nf[k], f[k]); }
+        }
+        if (r + nw < rows) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = lane * 8 + k * 256;
+                if (c < C) { ng[k] = V8<T>::load_raw(dy + (r + nw) * C + c); nf[k] = V8<T>::load_raw(x + (r + nw) * C + c); }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = lane * 8 + k * 256;
             if (c < C) {
-                V8<T>::load(dy + r * C + c, g[k]);
-                V8<T>::load(x + r * C + c, f[k]);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     f[k][e] = (f[k][e] - mu) * rs;              // xhat
-                    const float gw = g[k][e] * w[c + e];
+                    const float gw = g[k][e] * wr[k][e];
                     s1 += gw; s2 += gw * f[k][e];
                 }
             }
@@ -366,7 +410,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
                 float o[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    o[e] = rs * (g[k][e] * w[c + e] - s1 - f[k][e] * s2);
+                    o[e] = rs * (g[k][e] * wr[k][e] - s1 - f[k][e] * s2);
                     aw[k][e] += g[k][e] * f[k][e];
                     ab[k][e] += g[k][e];
                 }
@@ -1077,7 +1121,7 @@ extern "C" int pk_colsum(const void* x, int dtype, long long rows, int C, float*
 
 extern "C" int pk_layernorm_fwd(const void* x, void* y, int dtype, long long rows, int C, const float* w, const float* b, float eps,
                                 float* mean, float* rstd, void* stream) {
-    PK_CHECK_ARG(C % 8 == 0 && rows > 0, "C must be a multiple of 8");
+    PK_CHECK_ARG(C % 8 == 0 && rows > 0 && C <= 1024, "C must be a multiple of 8, <= 1024");
     const int grid = grid_for(rows, 8);
     PK_DISPATCH_T(dtype, (ln_fwd_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)x, (T*)y, rows, C, w, b, eps, mean, rstd)));
     DONE();

@@ -680,6 +680,27 @@ def _ldv(V):
 _FUSED_LSE = os.environ.get("PK_FUSED_LSE", "1") != "0"
 
 
+# measurement hook (bench.py): when set to a dict, single launches of the step are bracketed by CUDA events on the launching stream,
+# e.g. EVENT_TAPS["fc2_fwd"] = [(start, end), ...] -- the duration of that kernel INSIDE a real step, not in a loop of its own
+EVENT_TAPS = None
+
+
+class _Tap:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if EVENT_TAPS is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *exc):
+        if EVENT_TAPS is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            EVENT_TAPS.setdefault(self.name, []).append((self.s, e))
+
+
 def _joint_forward(enc, pred, model, want_lse=False):
     """factored gated joint -> (logits [B,T,U1,ldv] act dtype, saved state).  ``want_lse``: the fc2 GEMM also
     reduces every logits row to per-tile (max, sum-exp) pairs (state["row_lse"]) for the fused loss."""
@@ -704,8 +725,9 @@ def _joint_forward(enc, pred, model, want_lse=False):
     row_lse = None
     if want_lse and _FUSED_LSE and logits.dtype == torch.bfloat16 and V % 8 == 0:
         row_lse = torch.empty(K.row_lse_parts(R, V, 256), R, 2, dtype=torch.float32, device=enc.device)
-    gemm_parts([h_parts], [w2], logits.view(R, ldv)[:, :V], bias=fc2.bias.detach(), row_lse=row_lse,
-               **({"block_n": 256} if row_lse is not None else {}))
+    with _Tap("fc2_fwd"):
+        gemm_parts([h_parts], [w2], logits.view(R, ldv)[:, :V], bias=fc2.bias.detach(), row_lse=row_lse,
+                   **({"block_n": 256} if row_lse is not None else {}))
     state = dict(row_lse=row_lse, ex=ex, py=py, h_parts=h_parts, enc_parts=enc_parts, pred_parts=pred_parts, wx=wx, w2=w2, dims=(B, T, U1, H, V, ldv))
     return logits, state
 
@@ -800,8 +822,9 @@ class JointLossFn(torch.autograd.Function):
             costs, _ = K.rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=V, want_grad=False, row_lse=st.pop("row_lse"))
             return costs
         db2 = torch.empty(logits.shape[-1], dtype=torch.float32, device=logits.device)
-        costs, _ = K.rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=V, dlogits=logits, colsum=db2,
-                                       row_lse=st.pop("row_lse"))
+        with _Tap("rnnt_loss"):
+            costs, _ = K.rnnt_loss_fwd_bwd(logits, labels, frame_lens, label_lens, V=V, dlogits=logits, colsum=db2,
+                                           row_lse=st.pop("row_lse"))
         d_enc, d_pred = _joint_backward(logits, st, model, db2=db2)
         del logits, st
         ctx.save_for_backward(d_enc, d_pred)

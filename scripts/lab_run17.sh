@@ -1,0 +1,23 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+rm -f gpurun_out/parity_measured.jsonl
+timeout 1500 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
+timeout 300 python scripts/profile_step.py > gpurun_out/step_kernel_table.txt 2>&1
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err
+timeout 600 python bench.py --workload decode --steps 3 --warmup 3 > gpurun_out/bench_decode.json 2> gpurun_out/bench_decode.err
+timeout 600 python bench.py --workload mbr --steps 5 --warmup 3 > gpurun_out/bench_mbr.json 2> gpurun_out/bench_mbr.err
+timeout 400 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_train.json 2> gpurun_out/bench_ref_train.err
+timeout 400 python bench.py --impl reference --workload decode --steps 1 --warmup 0 > gpurun_out/bench_ref_decode.json 2> gpurun_out/bench_ref_decode.err
+tail -n 5 gpurun_out/pytest_gpu.log; tail -n 2 gpurun_out/smoke.log; head -n 3 gpurun_out/step_kernel_table.txt | tail -n 1
+python - <<'PY'
+import json
+for f in ["bench_train","bench_decode","bench_mbr","bench_ref_train","bench_ref_decode"]:
+    try:
+        d=json.loads([l for l in open("gpurun_out/%s.json"%f) if l.startswith("{")][-1])
+        print(f, {k:d.get(k) for k in ("value","ms_per_step","e2e","host_ms_per_step","clocks")})
+        print("   roofline", d.get("roofline")); print("   loss", d.get("roofline_loss")); print("   cpu", d.get("cpu_baseline")); print("   parity", d.get("parity_full_shape"))
+    except Exception as e: print(f, "ERR", e)
+PY
+for f in gpurun_out/bench_*.err; do tail -n 2 $f; done
