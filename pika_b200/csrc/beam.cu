@@ -187,7 +187,8 @@ PK_DEVICE void topk_insert(float (&v)[K], int (&ix)[K], float x, int id) {
     }
 }
 
-constexpr int ADV_THREADS = 256;
+constexpr int ADV_THREADS = 512;                    // 16 warps (128 registers each): the candidate scan is latency-bound, one CTA per utterance
+constexpr int ADV_LOADS = 12;                       // independent score loads in flight per thread
 
 template <int K>
 __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* __restrict__ word_probs, const int* __restrict__ t_idx,
@@ -202,13 +203,10 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
     __shared__ float s_rowscore[K];
     __shared__ float s_lmterm[K];            // lm_scorer_scale * lm_scores[k] (fp32 product, as the reference's tensor expression forms it)
     __shared__ int s_kill[K];
-    __shared__ float s_cv[ADV_THREADS * K];
-    __shared__ int s_ci[ADV_THREADS * K];
+    __shared__ float s_wv[ADV_THREADS / 32][K];     // per-warp top-K (sorted: value desc, index asc)
+    __shared__ int s_wi[ADV_THREADS / 32][K];
     __shared__ float s_best[K];
     __shared__ int s_besti[K];
-    __shared__ float s_redv[ADV_THREADS / 32];
-    __shared__ int s_redi[ADV_THREADS / 32];
-    __shared__ int s_redp[ADV_THREADS / 32];
 
     const int par_old = step & 1, par_new = par_old ^ 1;
     const int* cur_tok = st.next_ys + ((long long)step * B + b) * K;
@@ -217,77 +215,107 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
     int* new_hyp = st.hyp_tok + (((long long)par_new * B + b) * K) * L;
     int* new_len = st.hyp_len + ((long long)par_new * B + b) * K;
 
-    // ---- 1. which beam rows may have children
-    if (tid < K) {
-        s_rowscore[tid] = st.scores[b * K + tid];
-        s_lmterm[tid] = use_lm ? lm.scale * lm.lm_scores[b * K + tid] : 0.f;
-        int kill = 0;
-        if (step > 0) {
-            if (cur_tok[tid] == -1) kill = 1;                                  // finished beams have no children
-            else if (beam_prune && old_len[tid] > 0) {                          // duplicate partial hypothesis: first row wins
-                for (int j = 0; j < tid && !kill; ++j) {
-                    if (cur_tok[j] == -1 || old_len[j] != old_len[tid]) continue;
-                    bool same = true;
-                    for (int q = 0; q < old_len[tid]; ++q)
-                        if (old_hyp[(long long)j * L + q] != old_hyp[(long long)tid * L + q]) { same = false; break; }
-                    if (same) kill = 1;
+    // ---- 1. which beam rows may have children.  Warp i decides row i; the duplicate test (first row with the same partial hypothesis
+    // wins, decoder/beam_transducer.py:105-114) compares the two token rows 32 elements at a time.
+    {
+        const int wi = tid >> 5, ln = tid & 31;
+        if (wi < K) {
+            int kill = 0;
+            if (step > 0) {
+                if (cur_tok[wi] == -1) kill = 1;                                // finished beams have no children
+                else if (beam_prune && old_len[wi] > 0) {
+                    const int n = old_len[wi];
+                    for (int j = 0; j < wi && !kill; ++j) {
+                        if (cur_tok[j] == -1 || old_len[j] != n) continue;
+                        bool same = true;
+                        for (int q0 = 0; q0 < n && same; q0 += 32) {
+                            const int q = q0 + ln;
+                            const bool eq = q >= n || old_hyp[(long long)j * L + q] == old_hyp[(long long)wi * L + q];
+                            same = __all_sync(0xffffffffu, eq);
+                        }
+                        if (same) kill = 1;
+                    }
                 }
+            } else if (wi > 0) {
+                kill = 2;                                                       // first step: only row 0 is expanded
             }
-        } else if (tid > 0) {
-            kill = 2;                                                           // first step: only row 0 is expanded
+            if (ln == 0) {
+                s_kill[wi] = kill;
+                s_rowscore[wi] = st.scores[b * K + wi];
+                s_lmterm[wi] = use_lm ? lm.scale * lm.lm_scores[b * K + wi] : 0.f;
+            }
         }
-        s_kill[tid] = kill;
     }
     __syncthreads();
 
-    // ---- 2. per-thread top-K over the K*V candidates (flat index = k*V + v)
+    // ---- 2. per-thread top-K over the K*V candidates (flat index = k*V + v).  The scores were just written by the log-softmax kernel
+    // and sit in L2: ADV_LOADS independent loads are in flight per thread and iteration (one load per iteration left the scan waiting an L2
+    // round trip 375 times: 150 us per step at beam 16 x V = 6000).
     float lv[K];
     int li[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) { lv[j] = -INFINITY; li[j] = 0x7fffffff; }
     const float* wp = word_probs + (long long)b * K * V;
-    const int total = K * V;
-    for (int id = tid; id < total; id += ADV_THREADS) {
-        const int k = id / V;
-        float x;
-        if (s_kill[k] == 2) continue;
-        if (s_kill[k] == 1) x = kKill;
-        else if (step > 0) {
-            x = wp[id] + s_rowscore[k];                                      // word_probs + scores (+ lm term, in this order: beam_transducer.py:94-97)
-            if (use_lm) x += s_lmterm[k];
-        } else x = wp[id];
-        topk_insert<K>(lv, li, x, id);
-    }
-#pragma unroll
-    for (int j = 0; j < K; ++j) { s_cv[tid * K + j] = lv[j]; s_ci[tid * K + j] = li[j]; }
-    __syncthreads();
-    // ---- 3. K rounds of block-wide arg-max over the ADV_THREADS*K candidates (value desc, index asc)
-    for (int round = 0; round < K; ++round) {
-        float bv = -INFINITY; int bi = 0x7fffffff, bp = -1;
-        for (int p = tid; p < ADV_THREADS * K; p += ADV_THREADS) {
-            const float v = s_cv[p]; const int ii = s_ci[p];
-            if (ii != 0x7fffffff && (v > bv || (v == bv && ii < bi) || bp < 0)) { bv = v; bi = ii; bp = p; }
+    for (int k = 0; k < K; ++k) {                                              // row by row: no index division, the row's kill flag and
+        const int kill = s_kill[k];                                             // score are loop invariants; a thread still sees its
+        if (kill == 2) continue;                                                // candidates in increasing flat index (ties keep order)
+        const float add = (step > 0) ? s_rowscore[k] : 0.f;
+        const float lmt = (step > 0 && use_lm) ? s_lmterm[k] : 0.f;
+        const float* wr = wp + (long long)k * V;
+        if (kill == 1) {                                                        // a finished / duplicate row: V candidates at -1e20
+            for (int v = tid; v < V; v += ADV_THREADS) topk_insert<K>(lv, li, kKill, k * V + v);
+            continue;
         }
+        for (int base = tid; base < V; base += ADV_LOADS * ADV_THREADS) {
+            float xs[ADV_LOADS];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-            if (op >= 0 && (bp < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bp = op; }
-        }
-        if ((tid & 31) == 0) { s_redv[tid >> 5] = bv; s_redi[tid >> 5] = bi; s_redp[tid >> 5] = bp; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < ADV_THREADS / 32; ++w) {
-                if (s_redp[w] >= 0 && (bp < 0 || s_redv[w] > bv || (s_redv[w] == bv && s_redi[w] < bi))) {
-                    bv = s_redv[w]; bi = s_redi[w]; bp = s_redp[w];
-                }
+            for (int u = 0; u < ADV_LOADS; ++u) {
+                const int v = base + u * ADV_THREADS;
+                xs[u] = v < V ? __ldg(wr + v) : -INFINITY;
             }
-            s_best[round] = bv; s_besti[round] = bi;
-            if (bp >= 0) s_ci[bp] = 0x7fffffff;                                 // consume
+#pragma unroll
+            for (int u = 0; u < ADV_LOADS; ++u) {
+                const int v = base + u * ADV_THREADS;
+                if (v >= V) continue;
+                float x = xs[u];
+                if (step > 0) {
+                    x = x + add;                                             // word_probs + scores (+ lm term, in this order: beam_transducer.py:94-97)
+                    if (use_lm) x += lmt;
+                }
+                topk_insert<K>(lv, li, x, k * V + v);
+            }
         }
-        __syncthreads();
     }
+    // ---- 3. merge: K rounds of warp arg-max over the heads of the 32 sorted lists of a warp (value desc, index asc; the winner shifts
+    // its list), then the same over the 32 warp lists by warp 0 -- registers and shuffles only, two block barriers in all
+    auto warp_merge = [&](float (&v)[K], int (&ix)[K], float* out_v, int* out_i) {
+        const int ln = tid & 31;
+        for (int round = 0; round < K; ++round) {
+            float bv = v[0];
+            int bi = ix[0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+            }
+            if (ln == 0) { out_v[round] = bv; out_i[round] = bi; }
+            if (bi != 0x7fffffff && ix[0] == bi) {                             // candidate indices are unique: exactly one lane consumed
+#pragma unroll
+                for (int j = 0; j < K - 1; ++j) { v[j] = v[j + 1]; ix[j] = ix[j + 1]; }
+                v[K - 1] = -INFINITY; ix[K - 1] = 0x7fffffff;
+            }
+        }
+    };
+    warp_merge(lv, li, s_wv[tid >> 5], s_wi[tid >> 5]);
+    __syncthreads();
+    if (tid < 32) {
+        const bool has = tid < ADV_THREADS / 32;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { lv[j] = has ? s_wv[has ? tid : 0][j] : -INFINITY; li[j] = has ? s_wi[has ? tid : 0][j] : 0x7fffffff; }
+        warp_merge(lv, li, s_best, s_besti);
+    }
+    __syncthreads();
 
     // ---- 4. new beam: back-pointers, tokens, scores, finish rule, partial hypotheses
     int* out_tok = st.next_ys + ((long long)(step + 1) * B + b) * K;

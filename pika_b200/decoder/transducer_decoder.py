@@ -43,7 +43,9 @@ class _Workspace:
         L = m.decoder.num_layers if dec.xf is False else 0         # transformer prediction net: no recurrent state (see _xf_states)
         E = m.embed.weight.shape[1]
         self.H, self.V, self.L, self.E = H, V, L, E
-        self.ldx = (E + 7) // 8 * 8
+        # layer 0 reads the embedding row zero-padded to the hidden width, so that x W_ih^T + h W_hh^T of a layer is ONE GEMM launch with two
+        # accumulated (A, B) pairs (pairs share the reduction extent); the padding columns of x and of the staged W_ih are zero
+        self.ldx = H if (E <= H and not dec.xf) else (E + 7) // 8 * 8
         rows = self.rows = B * Kb
         i32 = lambda *s, fill=0: torch.full(s, fill, dtype=torch.int32, device=dev)     # noqa: E731
         f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)                # noqa: E731
@@ -194,8 +196,11 @@ class TransducerDecoder():
                                   P(m.embed.weight.detach()), ws.E, P(ws.x_emb), ws.ldx, Kb, blk, rows, st()), "pk_beam_prepare")
         xin = ws.x_emb
         for l in range(L):
-            engine.gemm_parts([engine.stage_act(xin)], [ws.w_ih[l]], ws.gates, bias=ws.bsum[l])
-            engine.gemm_parts([engine.stage_act(h[l])], [ws.w_hh[l]], ws.gates, accumulate=True, k_splits=1)
+            if xin.shape[1] == H:
+                engine.gemm_parts([engine.stage_act(xin), engine.stage_act(h[l])], [ws.w_ih[l], ws.w_hh[l]], ws.gates, bias=ws.bsum[l])
+            else:
+                engine.gemm_parts([engine.stage_act(xin)], [ws.w_ih[l]], ws.gates, bias=ws.bsum[l])
+                engine.gemm_parts([engine.stage_act(h[l])], [ws.w_hh[l]], ws.gates, accumulate=True, k_splits=1)
             check(lib.pk_beam_lstm_cell(P(ws.gates), P(ws.next_ys), P(ws.step_ctx), blk, P(h[l]), dt, P(c[l]), rows, H, st()), "pk_beam_lstm_cell")
             xin = h[l]
         dec_hid = self._xf_states(ws, par) if self.xf else h[L - 1]
@@ -329,19 +334,24 @@ class TransducerDecoder():
         fc = ws.fin_count.cpu().numpy()
         nmax = max(int(fc.max()) if B else 0, 1)
         fs, fstep, fk = ws.fin_score[:, :nmax].cpu().numpy(), ws.fin_step[:, :nmax].cpu().numpy(), ws.fin_k[:, :nmax].cpu().numpy()
-        ret = {"predictions": [], "scores": []}
+        # sort_finished (stable, like list.sort(key=-score)) per utterance, then every selected hypothesis walks its back-pointers at once
+        # (BeamMergeTransducer.get_hyp): one numpy gather per beam step instead of a Python loop per token
+        sel = []                                                              # (utterance, slot in the finished list)
         for b in range(B):
-            n = int(fc[b])
-            order = sorted(range(n), key=lambda i: -fs[b, i])                 # stable, like list.sort(key=-score)
-            hyps, scs = [], []
-            for i in order[:self.n_best]:
-                k, toks = int(fk[b, i]), []
-                for j in range(int(fstep[b, i]) - 1, -1, -1):                 # BeamMergeTransducer.get_hyp
-                    toks.append(int(ny[j + 1, b, k]))
-                    k = int(pk[j, b, k])
-                toks = toks[::-1][:-1]                                        # strip the ending eos(-1)
-                hyps.append([torch.tensor(t, dtype=torch.long) for t in toks])
-                scs.append(torch.tensor(float(fs[b, i]), dtype=torch.float32))
-            ret["predictions"].append(hyps)
-            ret["scores"].append(scs)
+            order = sorted(range(int(fc[b])), key=lambda i: -fs[b, i])
+            sel.extend((b, i) for i in order[:self.n_best])
+        sb = np.asarray([b for b, _ in sel], np.int64)
+        si = np.asarray([i for _, i in sel], np.int64)
+        ln = fstep[sb, si].astype(np.int64) if len(sel) else np.zeros(0, np.int64)
+        kk = fk[sb, si].astype(np.int64) if len(sel) else np.zeros(0, np.int64)
+        toks = np.zeros((len(sel), int(ln.max()) if len(sel) else 0), np.int64)
+        for j in range(toks.shape[1] - 1, -1, -1):
+            act = ln > j
+            toks[act, j] = ny[j + 1, sb[act], kk[act]]
+            kk[act] = pk[j, sb[act], kk[act]]
+        ret = {"predictions": [[] for _ in range(B)], "scores": [[] for _ in range(B)]}
+        for r, (b, i) in enumerate(sel):
+            hyp = torch.from_numpy(toks[r, :max(int(ln[r]) - 1, 0)].copy())   # strip the ending eos(-1)
+            ret["predictions"][b].append(list(hyp.unbind(0)))                 # 0-d int64 tensors, like the reference's token lists
+            ret["scores"][b].append(torch.tensor(float(fs[b, i]), dtype=torch.float32))
         return ret, enc.float()
