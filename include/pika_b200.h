@@ -265,10 +265,13 @@ int pk_beam_lstm_cell(const float* gates, const int* next_ys, const int* step_ct
                       void* stream);
 int pk_beam_step_end(int* step_ctx, const int* not_done, int max_steps, void* stream);
 int pk_beam_gate(const float* a, void* h, int dtype, int rows, int H, void* stream);
-/* one BeamMergeTransducer.advance for every utterance: word_probs [B*K, V] f32 log-probs, t_idx [B*K],
- * histories next_ys [S+1,B,K], prev_ks [S,B,K]; partial hypotheses hyp_tok [2,B,K,L] / hyp_len [2,B,K];
+/* one BeamMergeTransducer.advance for every utterance.  The word scores are given as the joint's logits [B*K rows, pitch ldv] f32 plus
+ * the per-row log-sum-exp of sm_scale * logits (pk_row_lse): word_probs[r, v] = logits[r, v] * sm_scale - row_lse[r], the very expression
+ * pk_log_softmax evaluates (decoder/transducer_decoder.py:177), formed on the fly so that the [B*K, V] log-prob tensor is never written.
+ * t_idx [B*K], histories next_ys [S+1,B,K], prev_ks [S,B,K]; partial hypotheses hyp_tok [2,B,K,L] / hyp_len [2,B,K];
  * finished lists fin_* [B,cap]; *not_done_total is decremented when an utterance becomes done. */
-int pk_beam_advance(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+int pk_row_lse(const void* x, int dtype, long long ld, float* lse, long long rows, int n, float scale, void* stream);
+int pk_beam_advance(const float* logits, int ldv, const float* row_lse, float sm_scale, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
                     int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
                     int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
                     const int* step_ctx, int blk, int n_best, int beam_prune, void* stream);
@@ -288,7 +291,7 @@ typedef struct {
     int backoff_id, n_disambig;
     int disambig_ids[4];
 } pk_lm_fst;
-int pk_beam_advance_lm(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+int pk_beam_advance_lm(const float* logits, int ldv, const float* row_lse, float sm_scale, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
                        int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
                        int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
                        const int* step_ctx, int blk, int n_best, int beam_prune, const pk_lm_fst* fst, double lm_scale, double nonblk_reward,

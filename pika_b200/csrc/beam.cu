@@ -191,7 +191,8 @@ constexpr int ADV_THREADS = 512;                    // 16 warps (128 registers e
 constexpr int ADV_LOADS = 12;                       // independent score loads in flight per thread
 
 template <int K>
-__global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* __restrict__ word_probs, const int* __restrict__ t_idx,
+__global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* __restrict__ logits, int ldv, const float* __restrict__ row_lse,
+                                                                   float sm_scale, const int* __restrict__ t_idx,
                                                                    const int* __restrict__ num_frames, const int* __restrict__ max_len,
                                                                    BeamState st, int B, int V, int L, int cap, StepCtx ctx, int blk,
                                                                    int n_best, int beam_prune, LmArgs lm) {
@@ -207,6 +208,8 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
     __shared__ int s_wi[ADV_THREADS / 32][K];
     __shared__ float s_best[K];
     __shared__ int s_besti[K];
+    __shared__ float s_lse[K];
+    __shared__ int s_oldlen[K];
 
     const int par_old = step & 1, par_new = par_old ^ 1;
     const int* cur_tok = st.next_ys + ((long long)step * B + b) * K;
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
     int* new_hyp = st.hyp_tok + (((long long)par_new * B + b) * K) * L;
     int* new_len = st.hyp_len + ((long long)par_new * B + b) * K;
 
+    const int* hyp_src = old_hyp;
     // ---- 1. which beam rows may have children.  Warp i decides row i; the duplicate test (first row with the same partial hypothesis
     // wins, decoder/beam_transducer.py:105-114) compares the two token rows 32 elements at a time.
     {
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
                         bool same = true;
                         for (int q0 = 0; q0 < n && same; q0 += 32) {
                             const int q = q0 + ln;
-                            const bool eq = q >= n || old_hyp[(long long)j * L + q] == old_hyp[(long long)wi * L + q];
+                            const bool eq = q >= n || hyp_src[(long long)j * L + q] == hyp_src[(long long)wi * L + q];
                             same = __all_sync(0xffffffffu, eq);
                         }
                         if (same) kill = 1;
@@ -241,6 +245,8 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
             }
             if (ln == 0) {
                 s_kill[wi] = kill;
+                s_lse[wi] = row_lse[b * K + wi];
+                s_oldlen[wi] = old_len[wi];
                 s_rowscore[wi] = st.scores[b * K + wi];
                 s_lmterm[wi] = use_lm ? lm.scale * lm.lm_scores[b * K + wi] : 0.f;
             }
@@ -248,44 +254,74 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
     }
     __syncthreads();
 
-    // ---- 2. per-thread top-K over the K*V candidates (flat index = k*V + v).  The scores were just written by the log-softmax kernel
-    // and sit in L2: ADV_LOADS independent loads are in flight per thread and iteration (one load per iteration left the scan waiting an L2
-    // round trip 375 times: 150 us per step at beam 16 x V = 6000).
+    // ---- 2. per-thread top-K over the K*V candidates (flat index = k*V + v).  The scores sit in L2 (the joint GEMM just wrote them): a
+    // thread's candidates of one row arrive as ADV_LOADS / 4 independent 16-byte loads, and the next batch is already in flight while this
+    // one is visited (the first version, one scalar load per iteration, waited an L2 round trip 375 times: 150 us per step at beam 16 x
+    // V = 6000).  word_probs[k, v] = log_softmax(sm_scale * logits)[k, v] = logits[k, v] * sm_scale - row_lse[k] is formed here with the
+    // expression pk_log_softmax uses, so the candidate scores are the ones a separate log-softmax pass would have written (not run).
+    // Tried on top of this and measured no better (profiles/r02_notes.md): a two-pass threshold filter (the list insertion is executed by
+    // a warp whenever ANY lane inserts), two CTAs per utterance, hypotheses staged in shared memory for the duplicate test.
     float lv[K];
     int li[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) { lv[j] = -INFINITY; li[j] = 0x7fffffff; }
-    const float* wp = word_probs + (long long)b * K * V;
-    for (int k = 0; k < K; ++k) {                                              // row by row: no index division, the row's kill flag and
-        const int kill = s_kill[k];                                             // score are loop invariants; a thread still sees its
-        if (kill == 2) continue;                                                // candidates in increasing flat index (ties keep order)
-        const float add = (step > 0) ? s_rowscore[k] : 0.f;
-        const float lmt = (step > 0 && use_lm) ? s_lmterm[k] : 0.f;
-        const float* wr = wp + (long long)k * V;
-        if (kill == 1) {                                                        // a finished / duplicate row: V candidates at -1e20
-            for (int v = tid; v < V; v += ADV_THREADS) topk_insert<K>(lv, li, kKill, k * V + v);
-            continue;
-        }
-        for (int base = tid; base < V; base += ADV_LOADS * ADV_THREADS) {
-            float xs[ADV_LOADS];
+    const float* wp = logits + (long long)b * K * ldv;
+    // a batch = ADV_LOADS candidates per thread as ADV_LOADS / 4 16-byte loads (4 consecutive labels each): (row it / nb, batch it % nb)
+    const int nb = (V + ADV_LOADS * ADV_THREADS - 1) / (ADV_LOADS * ADV_THREADS);
+    const bool vec_ok = (ldv % 4) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0;
+    auto fetch = [&](int k, int bi, float (&xs)[ADV_LOADS]) {
+        if (k >= K || s_kill[k] != 0) return;
+        const float* wr = wp + (long long)k * ldv;
 #pragma unroll
-            for (int u = 0; u < ADV_LOADS; ++u) {
-                const int v = base + u * ADV_THREADS;
-                xs[u] = v < V ? __ldg(wr + v) : -INFINITY;
+        for (int u4 = 0; u4 < ADV_LOADS / 4; ++u4) {
+            const int v = (bi * (ADV_LOADS / 4) + u4) * 4 * ADV_THREADS + 4 * tid;
+            if (vec_ok && v + 3 < V) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(wr + v));
+                xs[4 * u4] = q.x; xs[4 * u4 + 1] = q.y; xs[4 * u4 + 2] = q.z; xs[4 * u4 + 3] = q.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) xs[4 * u4 + e] = (v + e < V) ? __ldg(wr + v + e) : -INFINITY;
             }
+        }
+    };
+    auto scan = [&](auto&& visit) {                                            // visit(x, flat index) for every candidate of this thread,
+        float cur[ADV_LOADS], n1[ADV_LOADS];                                    // in increasing flat index (ties keep their order)
+        int k = 0, bi = 0, k1 = 0, b1 = 0;
+        auto next = [&](int& kk, int& bb) { if (++bb == nb) { bb = 0; ++kk; } };
+        fetch(k, bi, cur);
+        k1 = k; b1 = bi; next(k1, b1); fetch(k1, b1, n1);
+        while (k < K) {
+            const int kill = s_kill[k];
+            if (kill == 0) {
+                const float add = (step > 0) ? s_rowscore[k] : 0.f;
+                const float lmt = (step > 0 && use_lm) ? s_lmterm[k] : 0.f;
+                const float lse_k = s_lse[k];
 #pragma unroll
-            for (int u = 0; u < ADV_LOADS; ++u) {
-                const int v = base + u * ADV_THREADS;
-                if (v >= V) continue;
-                float x = xs[u];
-                if (step > 0) {
-                    x = x + add;                                             // word_probs + scores (+ lm term, in this order: beam_transducer.py:94-97)
-                    if (use_lm) x += lmt;
+                for (int u = 0; u < ADV_LOADS; ++u) {
+                    const int v = (bi * (ADV_LOADS / 4) + (u >> 2)) * 4 * ADV_THREADS + 4 * tid + (u & 3);
+                    if (v >= V) continue;
+                    float x = cur[u] * sm_scale - lse_k;
+                    if (step > 0) {
+                        x = x + add;                                         // word_probs + scores (+ lm term, in this order: beam_transducer.py:94-97)
+                        if (use_lm) x += lmt;
+                    }
+                    visit(x, k * V + v);
                 }
-                topk_insert<K>(lv, li, x, k * V + v);
-            }
+            } else if (kill == 1) {                                             // a finished / duplicate row: V candidates at -1e20
+#pragma unroll
+                for (int u = 0; u < ADV_LOADS; ++u) {
+                    const int v = (bi * (ADV_LOADS / 4) + (u >> 2)) * 4 * ADV_THREADS + 4 * tid + (u & 3);
+                    if (v < V) visit(kKill, k * V + v);
+                }
+            }                                                                   // kill == 2 (first step, rows > 0): no candidates
+#pragma unroll
+            for (int u = 0; u < ADV_LOADS; ++u) cur[u] = n1[u];
+            k = k1; bi = b1;
+            next(k1, b1);
+            fetch(k1, b1, n1);
         }
-    }
+    };
+    scan([&](float x, int id) { topk_insert<K>(lv, li, x, id); });
     // ---- 3. merge: K rounds of warp arg-max over the heads of the 32 sorted lists of a warp (value desc, index asc; the winner shifts
     // its list), then the same over the 32 warp lists by warp 0 -- registers and shuffles only, two block barriers in all
     auto warp_merge = [&](float (&v)[K], int (&ix)[K], float* out_v, int* out_i) {
@@ -395,8 +431,8 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
     for (int k = 0; k < K; ++k) {
         const int pk = s_besti[k] / V, y = s_besti[k] - (s_besti[k] / V) * V;
         const int src = s_fin[k] ? k : pk;
-        const int n = old_len[src];
-        for (int q = tid; q < n; q += ADV_THREADS) new_hyp[(long long)k * L + q] = old_hyp[(long long)src * L + q];
+        const int n = s_oldlen[src];
+        for (int q = tid; q < n; q += ADV_THREADS) new_hyp[(long long)k * L + q] = hyp_src[(long long)src * L + q];
         if (tid == 0) {
             int nn = n;
             if (!s_fin[k] && y != blk && nn < L) { new_hyp[(long long)k * L + nn] = y; ++nn; }
@@ -453,15 +489,19 @@ extern "C" int pk_beam_gate(const float* a, void* h, int dtype, int rows, int H,
     PK_CHECK_LAUNCH(); count_launch();
     return 0;
 }
-static int beam_advance_impl(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+static int beam_advance_impl(const float* logits, int ldv, const float* row_lse, float sm_scale, const int* t_idx, const int* num_frames,
+                             const int* max_len, float* scores,
                              int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
                              int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
                              const int* step_ctx, int blk, int n_best, int beam_prune, const LmArgs& lm, void* stream) {
     const StepCtx step{step_ctx};
     BeamState st{scores, next_ys, prev_ks, hyp_tok, hyp_len, fin_score, fin_step, fin_k, fin_count, eos_top, done, not_done_total};
     PK_CHECK_ARG(V >= K, "vocabulary smaller than the beam");
+    PK_CHECK_ARG(ldv >= V && row_lse != nullptr, "logits pitch smaller than V, or no row log-sum-exp");
+    // (two CTAs per utterance -- a cluster, each scanning every other row, top-K handed over through distributed shared memory -- measured
+    //  slower than one: 54.5 vs 49 us; the scan was bound by the divergent list insertion, not by the number of SMs)
     switch (K) {
-#define CASE(KK) case KK: beam_advance_kernel<KK><<<B, ADV_THREADS, 0, ST(stream)>>>(word_probs, t_idx, num_frames, max_len, st, B, V, L, cap, step, blk, n_best, beam_prune, lm); break;
+#define CASE(KK) case KK: beam_advance_kernel<KK><<<B, ADV_THREADS, 0, ST(stream)>>>(logits, ldv, row_lse, sm_scale, t_idx, num_frames, max_len, st, B, V, L, cap, step, blk, n_best, beam_prune, lm); break;
         CASE(1) CASE(2) CASE(4) CASE(8) CASE(16)
 #undef CASE
         default: PK_CHECK_ARG(false, "beam size must be 1, 2, 4, 8 or 16");
@@ -469,15 +509,15 @@ static int beam_advance_impl(const float* word_probs, const int* t_idx, const in
     PK_CHECK_LAUNCH(); count_launch();
     return 0;
 }
-extern "C" int pk_beam_advance(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+extern "C" int pk_beam_advance(const float* logits, int ldv, const float* row_lse, float sm_scale, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
                                int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
                                int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
                                const int* step, int blk, int n_best, int beam_prune, void* stream) {
     LmArgs lm{};
-    return beam_advance_impl(word_probs, t_idx, num_frames, max_len, scores, next_ys, prev_ks, hyp_tok, hyp_len, fin_score, fin_step, fin_k,
+    return beam_advance_impl(logits, ldv, row_lse, sm_scale, t_idx, num_frames, max_len, scores, next_ys, prev_ks, hyp_tok, hyp_len, fin_score, fin_step, fin_k,
                              fin_count, eos_top, done, not_done_total, B, K, V, L, cap, step, blk, n_best, beam_prune, lm, stream);
 }
-extern "C" int pk_beam_advance_lm(const float* word_probs, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
+extern "C" int pk_beam_advance_lm(const float* logits, int ldv, const float* row_lse, float sm_scale, const int* t_idx, const int* num_frames, const int* max_len, float* scores,
                                   int* next_ys, int* prev_ks, int* hyp_tok, int* hyp_len, float* fin_score, int* fin_step, int* fin_k,
                                   int* fin_count, int* eos_top, int* done, int* not_done_total, int B, int K, int V, int L, int cap,
                                   const int* step, int blk, int n_best, int beam_prune, const pk_lm_fst* fst, double lm_scale, double nonblk_reward,
@@ -492,7 +532,7 @@ extern "C" int pk_beam_advance_lm(const float* word_probs, const int* t_idx, con
     for (int i = 0; i < fst->n_disambig; ++i) lm.disambig[i] = fst->disambig_ids[i];
     lm.scale = (float)lm_scale; lm.scale_d = lm_scale; lm.reward = nonblk_reward;
     lm.set_state = set_state; lm.set_cost = set_cost; lm.set_n = set_n; lm.lm_scores = lm_scores; lm.MS = max_states; lm.err = err_flag;
-    return beam_advance_impl(word_probs, t_idx, num_frames, max_len, scores, next_ys, prev_ks, hyp_tok, hyp_len, fin_score, fin_step, fin_k,
+    return beam_advance_impl(logits, ldv, row_lse, sm_scale, t_idx, num_frames, max_len, scores, next_ys, prev_ks, hyp_tok, hyp_len, fin_score, fin_step, fin_k,
                              fin_count, eos_top, done, not_done_total, B, K, V, L, cap, step, blk, n_best, beam_prune, lm, stream);
 }
 extern "C" int pk_beam_reorder(const int* prev_ks, const int* step_ctx, const void* h_in, const float* c_in, const int* t_in, void* h_out, float* c_out,

@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const
 // log_softmax rows: x T [rows, ld] (first n valid) -> y f32 [rows, n] * 1
 template <typename T>
 __global__ void __launch_bounds__(256) log_softmax_kernel(const T* __restrict__ x, long long ld, float* __restrict__ y, long long rows,
-                                                          int n, float scale) {
+                                                          int n, float scale, float* __restrict__ lse = nullptr) {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
@@ -622,7 +622,8 @@ __global__ void __launch_bounds__(256) log_softmax_kernel(const T* __restrict__ 
         float s = 0.f;
         for (int c = lane; c < n; c += 32) s += expf(to_f32<T>(xr[c]) * scale - m);
         const float l = m + logf(warp_sum(s));
-        for (int c = lane; c < n; c += 32) y[r * n + c] = to_f32<T>(xr[c]) * scale - l;
+        if (y) for (int c = lane; c < n; c += 32) y[r * n + c] = to_f32<T>(xr[c]) * scale - l;
+        if (lse && lane == 0) lse[r] = l;                          // y[r, c] == x[r, c] * scale - lse[r], bit for bit (same expression)
     }
 }
 
@@ -1194,6 +1195,11 @@ extern "C" int pk_add(const void* a, const void* b, void* o, int dtype, long lon
 extern "C" int pk_log_softmax(const void* x, int dtype, long long ld, float* y, long long rows, int n, float scale, void* stream) {
     const int grid = grid_for(rows, 8);
     PK_DISPATCH_T(dtype, (log_softmax_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)x, ld, y, rows, n, scale)));
+    DONE();
+}
+extern "C" int pk_row_lse(const void* x, int dtype, long long ld, float* lse, long long rows, int n, float scale, void* stream) {
+    const int grid = grid_for(rows, 8);
+    PK_DISPATCH_T(dtype, (log_softmax_kernel<T><<<grid, 256, 0, STREAM(stream)>>>((const T*)x, ld, nullptr, rows, n, scale, lse)));
     DONE();
 }
 

@@ -52,7 +52,6 @@ PK_DEVICE void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uin
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
-PK_DEVICE uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 PK_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // mode 0: membar.gl + relaxed atomic + volatile polling + membar.gl (round 1).  mode 1 (default): release reduction, acquire polling loads

@@ -70,7 +70,7 @@ class _Workspace:
         self.hj = torch.empty(rows, H, dtype=adt, device=dev)
         self.ldv = (V + 3) // 4 * 4
         self.logits = f32(rows, self.ldv)
-        self.wp = f32(rows, V)
+        self.row_lse = f32(rows)
         self.step_ctx = i32(2)
         # staged weights at fixed addresses: re-filled from the live parameters at every decode_batch (the MBR trainer updates them
         # between calls), [hi] in bf16 production mode, [hi, lo] in the fp32-class parity mode
@@ -208,8 +208,10 @@ class TransducerDecoder():
                           [[p[:, :H] for p in ws.wx], [p[:, H:] for p in ws.wx]], ws.pre, bias=ws.bx)
         check(lib.pk_beam_gate(P(ws.pre), P(ws.hj), K._dt(ws.hj), rows, H, st()), "pk_beam_gate")
         engine.gemm_parts([engine.stage_act(ws.hj)], [ws.w2], ws.logits[:, :V], bias=ws.b2)
-        K.log_softmax(ws.logits, ws.wp, V, self.sm_scale)
-        common = (P(ws.wp), P(t_idx), P(ws.nf), P(ws.ml), P(ws.scores), P(ws.next_ys), P(ws.prev_ks), P(ws.hyp_tok), P(ws.hyp_len),
+        # log_softmax(sm_scale * logits) is not materialised: one pass leaves the row log-sum-exp, pk_beam_advance forms the log-probs
+        check(lib.pk_row_lse(P(ws.logits), K._dt(ws.logits), ctypes.c_longlong(ws.ldv), P(ws.row_lse), ctypes.c_longlong(rows), V,
+                             ctypes.c_float(self.sm_scale), st()), "pk_row_lse")
+        common = (P(ws.logits), ws.ldv, P(ws.row_lse), ctypes.c_float(self.sm_scale), P(t_idx), P(ws.nf), P(ws.ml), P(ws.scores), P(ws.next_ys), P(ws.prev_ks), P(ws.hyp_tok), P(ws.hyp_len),
                   P(ws.fin_score), P(ws.fin_step), P(ws.fin_k), P(ws.fin_count), P(ws.eos_top), P(ws.done), P(ws.not_done), ws.B, Kb, V,
                   ws.Scap + 1, ws.cap, P(ws.step_ctx), blk, self.n_best, int(bool(self.beam_prune)))
         if ws.lm is None:
