@@ -10,7 +10,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_train_cli_two_epochs(tmp_path):
+@pytest.mark.parametrize("decoder_type", ["rnn", "transformer"])
+def test_train_cli_two_epochs(tmp_path, decoder_type):
+    """``--decoder_type transformer`` trains the convolutional-transformer prediction net (trainer/model/transducer.py:62-68)"""
     from test_loader_cpu import make_dataset
     from pika_b200.trainer import train_transducer_bmuf_otfaug as T
     lst, utts = make_dataset(tmp_path, n_utts=8, shards=1, n_lo=14000, n_hi=22000)
@@ -24,7 +26,7 @@ def test_train_cli_two_epochs(tmp_path):
     out.mkdir()
     log = tmp_path / "log.WORKER-ID"
     argv = ["transducer", lst.replace("data.lst", "data.lst"), str(log), str(out), "--cuda", "--local_rank", "0", "--encoder_type", "transformer",
-            "--decoder_type", "rnn", "--rnn_size", "1024", "--embd_dim", "100", "--output_dim", "60", "--padding_idx", "60", "--padding_tgt", "60",
+            "--decoder_type", decoder_type, "--rnn_size", "1024", "--embd_dim", "100", "--output_dim", "60", "--padding_idx", "60", "--padding_tgt", "60",
             "--dec_layers", "2", "--dropout", "0.0", "--brnn", "--model_lctx", "21", "--model_rctx", "21", "--model_stride", "4",
             "--lctx", "1", "--rctx", "1", "--feats_dim", "80", "--feat_config", str(cfg), "--cmn", "--cmvn_stats", str(cmvn), "--batch_size", "4",
             "--num_workers", "1", "--batch_first", "--max_len", "1600", "--TU_limit", "50000", "--gain_range", "25,25", "--speed_rate", "1.0", "--grad_clip", "3.0",
@@ -42,6 +44,7 @@ def test_train_cli_two_epochs(tmp_path):
         assert path.exists()
     m = torch.load(str(out / "model.epoch.4.0"), weights_only=False)
     assert m.fc2.weight.shape == (60, 1024) and bool(torch.isfinite(m.fc2.weight).all())
+    assert m.decoder_type == decoder_type and (decoder_type == "rnn" or hasattr(m.decoder, "linear_out"))
 
 
 def test_mbr_train_cli_one_epoch(tmp_path):
