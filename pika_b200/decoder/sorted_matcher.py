@@ -118,3 +118,26 @@ class SortedMatcher(object):
                     break
             fs.append(score); fst.append(cur)
         return fs, fst
+
+
+def read_fst_text(path):
+    """An acceptor / transducer in OpenFst TEXT form (``fstprint`` output: ``src dst ilabel [olabel] [weight]`` arc lines, ``state
+    [weight]`` final lines) -> the ``(arcs, finals)`` pair ``SortedMatcher`` takes, arcs of a state sorted by input label (``fstarcsort``
+    order).  Stands in for ``kaldi.fstext.StdVectorFst.read`` (decoder/decode_transducer.py:85), which needs PyKaldi: print the binary
+    LM once with ``fstprint`` and point ``--fst_lm`` at the text file."""
+    arcs, finals = {}, {}
+    n_states = 0
+    for line in open(path):
+        f = line.split()
+        if not f:
+            continue
+        if len(f) >= 3:
+            src, dst, il = int(f[0]), int(f[1]), int(f[2])
+            w = float(f[4]) if len(f) >= 5 else (float(f[3]) if len(f) == 4 and not f[3].lstrip("-").isdigit() else 0.0)
+            arcs.setdefault(src, []).append((il, w, dst))
+            n_states = max(n_states, src + 1, dst + 1)
+        else:
+            st = int(f[0])
+            finals[st] = float(f[1]) if len(f) == 2 else 0.0
+            n_states = max(n_states, st + 1)
+    return ([sorted(arcs.get(s, []), key=lambda a: a[0]) for s in range(n_states)], [finals.get(s, math.inf) for s in range(n_states)])

@@ -89,3 +89,106 @@ def iter_mrk_seq(mrk_fn, seq_fn):
             nb = int(p[2])
             nb -= nb % 2
             yield p[0], np.frombuffer(seq.read(nb), dtype="int16")
+
+
+# ------------------------------------------------------------------------------------------------ float matrix tables
+def _read_token(f):
+    tok = b""
+    while True:
+        c = f.read(1)
+        if not c:
+            return None if not tok else tok.decode()
+        if c in b" \n\t\r":
+            if tok:
+                return tok.decode()
+            continue
+        tok += c
+
+
+def _read_binary_matrix(f):
+    """after ``\\0B``: 'FM ' | 'DM ' , \\4 <int32 rows> \\4 <int32 cols>, row-major data (Kaldi's uncompressed matrix layout)"""
+    kind = f.read(3)
+    if kind not in (b"FM ", b"DM "):
+        raise NotImplementedError("Kaldi matrix type %r (compressed matrices are not written by the recipes' feature dumps)" % kind)
+    assert f.read(1) == b"\4"
+    rows = struct.unpack("<i", f.read(4))[0]
+    assert f.read(1) == b"\4"
+    cols = struct.unpack("<i", f.read(4))[0]
+    dt = np.float32 if kind == b"FM " else np.float64
+    return np.frombuffer(f.read(rows * cols * np.dtype(dt).itemsize), dtype=dt).reshape(rows, cols).astype(np.float32)
+
+
+def _read_text_matrix(f):
+    """`` [ r0c0 r0c1 ...\\n  r1c0 ... ]`` following a key"""
+    rows, cur = [], []
+    tok = _read_token(f)
+    assert tok == "[", "expected '[' at the start of a text matrix"
+    buf = b""
+    while True:
+        c = f.read(1)
+        if not c or c == b"]":
+            break
+        buf += c
+    for line in buf.decode().split("\n"):
+        vals = line.split()
+        if vals:
+            rows.append([float(v) for v in vals])
+    return np.asarray(rows, dtype=np.float32).reshape(len(rows), -1)
+
+
+def read_float_matrix_table(rspec):
+    """Yields (uttid, float32 [frames, dim]) in file order from ``ark:path``, ``ark,t:path`` or ``scp:path`` (lines ``key path[:offset]``)
+    -- the native stand-in for kaldi.util.table.SequentialMatrixReader (loader/utt_loader.py:80,158)."""
+    kind = rspec.split(":", 1)[0] if ":" in rspec else "ark"
+    path = rspec.split(":", 1)[1] if ":" in rspec else rspec
+    if "scp" in kind:
+        for line in open(path):
+            line = line.strip()
+            if not line:
+                continue
+            key, loc = line.split(None, 1)
+            fn, off = loc, None
+            if ":" in loc and loc.rsplit(":", 1)[1].isdigit():
+                fn, off = loc.rsplit(":", 1)
+            with open(fn, "rb") as f:
+                if off is not None:
+                    f.seek(int(off))                           # offset of the matrix itself (what copy-feats writes into an scp)
+                else:
+                    _read_token(f)                             # a file holding "key <matrix>"
+                pos = f.tell()
+                if f.read(2) == b"\0B":
+                    yield key, _read_binary_matrix(f)
+                else:
+                    f.seek(pos)
+                    yield key, _read_text_matrix(f)
+        return
+    with open(path, "rb") as f:
+        while True:
+            key = _read_token(f)
+            if key is None:
+                break
+            pos = f.tell()
+            if f.read(2) == b"\0B":
+                yield key, _read_binary_matrix(f)
+            else:
+                f.seek(pos)
+                yield key, _read_text_matrix(f)
+
+
+def write_float_matrix_ark(path, items, text=False):
+    """(uttid, [frames, dim] array) pairs -> Kaldi archive (binary 'FM ' or text); returns {uttid: byte offset of the matrix} for an scp"""
+    offs = {}
+    with open(path, "wb") as f:
+        for key, mat in items:
+            mat = np.ascontiguousarray(mat, dtype=np.float32)
+            f.write(key.encode() + b" ")
+            offs[key] = f.tell()
+            if text:
+                f.write(b" [\n")
+                for r in mat:
+                    f.write(("  " + " ".join("%.7g" % v for v in r) + "\n").encode())
+                f.seek(f.tell() - 1)
+                f.write(b" ]\n")
+            else:
+                f.write(b"\0BFM \4" + struct.pack("<i", mat.shape[0]) + b"\4" + struct.pack("<i", mat.shape[1]) + mat.tobytes())
+    return offs

@@ -210,3 +210,70 @@ def test_las_rescoring_hooks_call_the_users_rescorer():
         lp = F.log_softmax(scale * net.dec_proj(out), dim=-1).squeeze(1)
         ref = lp[torch.arange(4), tgt[1:].view(-1)].tolist()
         np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_decode_cli_end_to_end(tmp_path):
+    """the drop-in decoding entry point (decoder/decode_transducer.py): pickled model + Kaldi feature / label tables + CMVN file + symbol
+    map -> N-best text file; the lines must be what a direct TransducerDecoder call on the same processed features gives"""
+    from fixture_utils import decode_fixture_reinit
+    from pika_b200 import engine
+    from pika_b200.decoder import decode_transducer as D
+    from pika_b200.decoder.beam_transducer import GlobalScorer
+    from pika_b200.decoder.transducer_decoder import TransducerDecoder
+    from pika_b200.loader import utt_loader as UL
+    from pika_b200.loader.kaldi_io import write_float_matrix_ark
+    from pika_b200.model.transducer import Net
+    V, nutt, bs, beam, nbest = 40, 4, 2, 4, 2
+    torch.manual_seed(777)
+    margs = types.SimpleNamespace(rnn_size=1024, local_rank=0, decoder_type="rnn", brnn=True, encoder_type="transformer", embd_dim=100,
+                                  padding_idx=V, dropout=0.2, dec_layers=2, enc_layers=9)
+    m = Net(margs, 240, V)
+    decode_fixture_reinit(m)
+    torch.save(m, str(tmp_path / "model.pt"))
+    rng = np.random.default_rng(5)
+    feats = [("u%d" % i, rng.standard_normal((int(rng.integers(90, 131)), 80)).astype(np.float32)) for i in range(nutt)]
+    write_float_matrix_ark(str(tmp_path / "feats.ark"), feats)
+    (tmp_path / "labels.ark").write_text("".join("%s 1 2\n" % k for k, _ in feats))
+    mean, var, n = rng.standard_normal(80) * 0.1, np.abs(rng.standard_normal(80)) * 0.2 + 0.9, 1000.0
+    (tmp_path / "cmvn.stats").write_text(" [\n  %s %g\n  %s 0 ]\n" % (" ".join("%g" % v for v in mean * n), n,
+                                                                    " ".join("%g" % v for v in (var + mean * mean) * n)))
+    (tmp_path / "symbols.txt").write_text("".join("<%d> %d\n" % (i, i) for i in range(V + 1)))
+    out = tmp_path / "hyp.txt"
+    argv = [str(tmp_path / "model.pt"), "ark:%s" % (tmp_path / "feats.ark"), "ark,t:%s" % (tmp_path / "labels.ark"), str(out), "--loader", "utt",
+            "--cuda", "--batch_first", "--batch_size", str(bs), "--beam_size", str(beam), "--n_best", str(nbest), "--lctx", "1", "--rctx", "1",
+            "--feats_dim", "80", "--max_len", "400", "--padding_tgt", str(V), "--cmn", "--cmvn_stats", str(tmp_path / "cmvn.stats"),
+            "--symbols_map", str(tmp_path / "symbols.txt"), "--model_lctx", "21", "--model_rctx", "21", "--model_stride", "4", "--min_len", "60",
+            "--output_scores"]
+    prec = engine.get_precision()
+    engine.set_precision("fp32")
+    try:
+        D.main(argv)
+        lines = out.read_text().splitlines()
+        assert len(lines) == nutt * nbest
+        # the same batches through the loader + decoder directly
+        la = argparse_ns = types.SimpleNamespace(lctx=1, rctx=1, max_len=400, batch_size=bs, padding_tgt=V, feats_dim=80, batch_first=True,
+                                               stride=1, queue_size=8, cuda=True, local_rank=0, ctc_target=False)
+        cm = np.array([[float(v) for v in r.split()] for r in (tmp_path / "cmvn.stats").read_text().replace("[", "").replace("]", "").strip().split("\n")])
+        mu = cm[0][:-1] / cm[0][-1]
+        sd = np.sqrt(cm[1][:-1] / cm[0][-1] - mu * mu)
+        off = torch.from_numpy(np.tile(-mu, 3)).cuda().float()
+        sc = torch.from_numpy(np.tile(1.0 / sd, 3)).cuda().float()
+        mg = m.cuda().eval()
+        dargs = types.SimpleNamespace(las_rescorer=None, las_rescorer_bw=None, bilas_rescorer=None, nonblk_reward=1.5)
+        dec = TransducerDecoder(mg, bs, beam, n_best=nbest, blk=0, global_scorer=GlobalScorer(), sm_scale=1.0, cuda=True, beam_prune=True, args=dargs)
+        want = []
+        for data, _, lens, _ in UL.dataloader("ark,t:%s" % (tmp_path / "labels.ark"), "ark:%s" % (tmp_path / "feats.ark"), False, la):
+            x = data - data.mean(dim=1, keepdim=True)
+            x = (x + off) * sc
+            tl = torch.from_numpy(lens).cuda() - 42
+            tl = tl // 4 + torch.ne(tl % 4, 0).int()
+            ret, _ = dec.decode_batch(x, tl, (tl + 100).tolist())
+            for i in range(bs):
+                for j in range(nbest):
+                    toks = [int(e.item()) for e in ret["predictions"][i][j] if e != 0]
+                    want.append("".join("<%d>" % t for t in toks))
+        got = [l.split(" ")[0] for l in lines]
+        assert got == want and any(len(g) > 0 for g in got)
+        assert all(np.isfinite(float(l.split(" ")[1])) for l in lines)      # --output_scores appends the beam score (`" {}".format(score)`)
+    finally:
+        engine.set_precision(prec)

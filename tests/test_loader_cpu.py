@@ -115,3 +115,66 @@ def test_kaldi_readers(tmp_path):
     mean, var = np.array([2.0, 4.0]), np.array([30 / 5 - 4.0, 100 / 5 - 16.0])
     np.testing.assert_allclose(off, np.tile(-mean, 3))
     np.testing.assert_allclose(sc, np.tile(1 / np.sqrt(var), 3))
+
+
+# ------------------------------------------------------------------------------------------------ offline feature loader (decode CLI)
+def _feature_tables(tmp_path, n_utts=5, dim=6, seed=3):
+    from pika_b200.loader.kaldi_io import write_float_matrix_ark
+    rng = np.random.default_rng(seed)
+    feats = [("utt%02d" % i, rng.standard_normal((int(rng.integers(9, 23)), dim)).astype(np.float32)) for i in range(n_utts)]
+    labels = [[int(v) for v in rng.integers(1, 30, int(rng.integers(1, 6)))] for _ in range(n_utts)]
+    ark = tmp_path / "feats.ark"
+    offs = write_float_matrix_ark(str(ark), feats)
+    (tmp_path / "feats.scp").write_text("".join("%s %s:%d\n" % (k, ark, offs[k]) for k, _ in feats))
+    write_float_matrix_ark(str(tmp_path / "feats.txt.ark"), feats, text=True)
+    (tmp_path / "labels.ark").write_text("".join("%s %s\n" % (k, " ".join(str(v) for v in l)) for (k, _), l in zip(feats, labels)))
+    return feats, labels
+
+
+def test_float_matrix_tables_roundtrip(tmp_path):
+    """binary 'FM ' archive, text archive and scp (key file:offset) all give back the matrices, in file order"""
+    from pika_b200.loader.kaldi_io import read_float_matrix_table
+    feats, _ = _feature_tables(tmp_path)
+    for rspec, tol in (("ark:%s" % (tmp_path / "feats.ark"), 0.0), ("scp:%s" % (tmp_path / "feats.scp"), 0.0),
+                       ("ark,t:%s" % (tmp_path / "feats.txt.ark"), 1e-5)):
+        got = list(read_float_matrix_table(rspec))
+        assert [k for k, _ in got] == [k for k, _ in feats]
+        for (_, a), (_, b) in zip(feats, got):
+            assert a.shape == b.shape and np.abs(a - b).max() <= tol
+
+
+def test_utt_loader_batches_follow_reference_protocol(tmp_path):
+    """loader/utt_loader.py:154-232: splice with edge repetition, stride, data padded with each utterance's last frame, labels with
+    padding_tgt, only FULL batches are emitted, iteration ends after the generator's None"""
+    from pika_b200.loader import utt_loader as UL
+    feats, labels = _feature_tables(tmp_path)
+    p = argparse.ArgumentParser()
+    UL.register(p)
+    a = p.parse_args(["--lctx", "1", "--rctx", "2", "--max_len", "40", "--batch_size", "2", "--padding_tgt", "33", "--feats_dim", "6",
+                      "--batch_first", "--stride", "2"])
+    a.cuda, a.local_rank = False, 0
+    assert UL.get_inputdim(a) == 6 * 4
+    batches = list(UL.dataloader("ark,t:%s" % (tmp_path / "labels.ark"), "scp:%s" % (tmp_path / "feats.scp"), False, a))
+    assert len(batches) == 2                                   # 5 utterances, batch 2: the fifth never fills a batch
+    for bi, (data, target, lens, ali_lens) in enumerate(batches):
+        assert data.dtype == torch.float32 and target.dtype == torch.int64
+        for r in range(2):
+            f, l = feats[2 * bi + r][1], labels[2 * bi + r]
+            n = f.shape[0]
+            ref = np.stack([np.concatenate([f[min(max(t + o, 0), n - 1)] for o in (-1, 0, 1, 2)]) for t in range(n)])[::2]
+            assert lens[r] == ref.shape[0] and ali_lens[r] == len(l)
+            np.testing.assert_array_equal(data[r, :lens[r]].numpy(), ref)
+            assert bool((data[r, lens[r]:] == torch.from_numpy(ref[-1])).all())          # last valid frame repeated
+            assert target[r, :len(l)].tolist() == l and bool((target[r, len(l):] == 33).all())
+        assert data.shape[1] == int(max(lens)) and target.shape[1] == int(max(ali_lens))
+
+
+def test_read_fst_text(tmp_path):
+    from pika_b200.decoder.sorted_matcher import SortedMatcher, read_fst_text
+    (tmp_path / "g.txt").write_text("0 1 5 5 0.5\n0 2 3 3 1.25\n1 0 1 1 0.75\n1 2 4 4\n2 1.5\n0\n")
+    arcs, finals = read_fst_text(str(tmp_path / "g.txt"))
+    assert arcs[0] == [(3, 1.25, 2), (5, 0.5, 1)] and arcs[1] == [(1, 0.75, 0), (4, 0.0, 2)] and arcs[2] == []
+    assert finals[0] == 0.0 and finals[2] == 1.5 and finals[1] == float("inf")
+    m = SortedMatcher((arcs, finals), 2, 6, 1, [])
+    sc, st = m.get_scores(1, 3)                                # no arc 3 in state 1 -> back off (label 1) to state 0, then arc 3
+    assert st == [2] and abs(sc[0] - 2.0) < 1e-12
