@@ -148,3 +148,36 @@ def test_dither_is_gaussian_counter_based_and_off_by_default_in_parity_runs():
     g1 = fe.fbank(loud, nf, T, dither=1.0, seed=1)
     diff = (g1 - g0).abs().max().item()
     assert 0.0 < diff < 0.05                         # 1 LSB-class noise against a 3000-amplitude signal moves log energies by < 5e-2
+
+
+def test_compute_global_cmvn_cli_matches_oracle(tmp_path):
+    """utils/compute_global_cmvn.py drop-in: the stats file (sums, sums of squares, frame count) over a synthetic .lst corpus against the
+    numpy oracle (oracle/frontend.py: augmentation + Kaldi fbank) fed with the same augmentation draws; the file must read back through
+    the trainer's CMVN reader"""
+    import random
+    from oracle import frontend as ofe
+    from test_loader_cpu import make_dataset
+    from pika_b200.loader import kaldi_io
+    from pika_b200.utils import compute_global_cmvn as C
+    lst, utts = make_dataset(tmp_path, n_utts=6, shards=2, n_lo=6000, n_hi=12000)
+    cfg = tmp_path / "fbank.conf"
+    cfg.write_text("--window-type=hamming\n--sample-frequency=16000\n--dither=0\n--low-freq=40\n--high-freq=-200\n--num-mel-bins=80\n")
+    out = tmp_path / "cmvn.stats"
+    random.seed(11); np.random.seed(11)
+    C.main([lst, str(out), "--feat_config", str(cfg), "--cmn", "--batch_size", "4"])
+    stats = kaldi_io.read_kaldi_text_matrix(str(out))
+    assert stats.shape == (2, 81) and stats[1, 80] == 0.0
+    random.seed(11); np.random.seed(11)
+    s1, s2, cnt = np.zeros(80), np.zeros(80), 0
+    for mrk_fn, seq_fn in [l.split()[:2] for l in open(lst)]:
+        for _, audio in kaldi_io.iter_mrk_seq(mrk_fn, seq_fn):
+            rate = [0.9, 1.0, 1.1][random.randint(0, 2)]
+            gain = float(np.random.uniform(-55, -10))
+            f = ofe.kaldi_fbank(ofe.augment(np.asarray(audio, np.int16), rate, gain).astype(np.float32)).astype(np.float64)
+            f = f - f.mean(axis=0, keepdims=True)
+            s1 += f.sum(0); s2 += (f * f).sum(0); cnt += f.shape[0]
+    assert stats[0, 80] == cnt
+    np.testing.assert_allclose(stats[1, :80], s2, rtol=2e-3)                    # second moments of the mean-removed log-mel energies
+    assert np.abs(stats[0, :80] - s1).max() < 1e-2 * cnt                        # per-utterance CMN: the sums are ~0 on both sides
+    off, scale = kaldi_io.cmvn_offset_scale(str(out), 3)
+    assert off.shape == (240,) and np.isfinite(scale).all()
