@@ -139,7 +139,7 @@ int pk_cast_split(const void* src, int src_dtype, long long ld_src, void* hi, vo
 /* dst[c, r] = src[r, c] for a bf16 matrix [rows, cols]: K-major copies of staged weights for the dgrad GEMMs
  * (the reference relies on cuBLAS's transposed-operand modes, e.g. nn.Linear backward). */
 int pk_transpose_bf16(const void* src, long long ld_src, void* dst, long long ld_dst, int rows, int cols, void* stream);
-/* Fused unmasked multi-head self-attention, head dim 64, bf16 (pika_b200/csrc/attention.cu):
+/* Fused unmasked multi-head self-attention, head dim 64, bf16 (pika_b200/csrc/attention_tc.cu):
  *   O = dropout(softmax(alpha * Q K^T)) V  per (batch, head)   -- MultiHeadedAttention.forward,
  *   trainer/model/modules/multi_headed_attn.py:199-223 (scale, softmax, dropout, context) and its autograd backward,
  * without materialising the [B, heads, T, T] score / probability tensors.

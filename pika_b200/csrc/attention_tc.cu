@@ -479,18 +479,6 @@ template <int MODE> static int launch_attn(const AttnTcParams& p, cudaStream_t s
 
 extern "C" int pk_attention_lse_stride(int T) { return (T + 63) / 64 * 64; }
 
-// the round-1 mma.sync kernels (attention.cu), kept behind PK_ATTN_TC=0 for same-box A/B timing only
-extern "C" int pk_attention_hmma_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, float* lse,
-                                     int B, int T, int heads, int dh, float alpha, float drop_p, uint32_t seed, void* stream);
-extern "C" int pk_attention_hmma_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
-                                     const void* dout, long long ld_dout, const float* lse, float* dsum_ws, void* dq, void* dk, void* dv,
-                                     long long ld_dqkv, int B, int T, int heads, int dh, float alpha, float drop_p, uint32_t seed, void* stream);
-static bool use_tc() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("PK_ATTN_TC"); v = e ? atoi(e) : 1; }
-    return v != 0;
-}
-
 #define ATTN_CHECKS()                                                                                                      \
     PK_CHECK_ARG(B > 0 && T > 0 && heads > 0, "bad dims");                                                                 \
     PK_CHECK_ARG(dh == 64, "fused attention supports head dim 64");                                                        \
@@ -502,7 +490,6 @@ extern "C" int pk_attention_fwd(const void* q, const void* k, const void* v, lon
                                 int B, int T, int heads, int dh, float alpha, float drop_p, uint32_t seed, void* stream) {
     using namespace pk;
     ATTN_CHECKS();
-    if (!use_tc()) return pk_attention_hmma_fwd(q, k, v, ld_qkv, out, ld_out, lse, B, T, heads, dh, alpha, drop_p, seed, stream);
     static thread_local AttnTcParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.T = T; p.heads = heads; p.Tpad = pk_attention_lse_stride(T); p.Tp2 = (T + 1) / 2;
@@ -521,8 +508,6 @@ extern "C" int pk_attention_bwd(const void* q, const void* k, const void* v, lon
     using namespace pk;
     ATTN_CHECKS();
     PK_CHECK_ARG(ld_dout % 8 == 0 && ld_dqkv % 8 == 0, "row strides must be multiples of 8 elements (16 bytes)");
-    if (!use_tc())
-        return pk_attention_hmma_bwd(q, k, v, ld_qkv, out, ld_out, dout, ld_dout, lse, dsum_ws, dq, dk, dv, ld_dqkv, B, T, heads, dh, alpha, drop_p, seed, stream);
     static thread_local AttnTcParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.T = T; p.heads = heads; p.Tpad = pk_attention_lse_stride(T); p.Tp2 = (T + 1) / 2;

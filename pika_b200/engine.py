@@ -492,7 +492,7 @@ class AttentionFn(torch.autograd.Function):
         masked = causal or key_pad is not None
         ctx.fused = _FUSED_ATTN and qkv.dtype == torch.bfloat16 and dh == 64 and not masked
         if ctx.fused:
-            # scores / probabilities never leave the SM (pika_b200/csrc/attention.cu)
+            # scores / probabilities never leave the SM (pika_b200/csrc/attention_tc.cu)
             qkv = qkv.contiguous()
             out = _new((B, T, D), like=qkv)
             lse = torch.zeros(B * heads * K.attention_lse_stride(T), dtype=torch.float32, device=qkv.device)   # pad entries finite

@@ -350,7 +350,7 @@ def test_fused_lse_joint_loss_matches_separate_first_pass():
 
 @pytest.mark.parametrize("heads,T,B", [(4, 50, 2), (2, 200, 2), (16, 333, 1), (1, 64, 1), (3, 129, 2)])
 def test_fused_attention_bf16_matches_torch(heads, T, B):
-    """bf16 production path, head dim 64: attention.cu (scores stay on chip) vs fp32 torch on the same bf16 inputs."""
+    """bf16 production path, head dim 64: attention_tc.cu (scores stay on chip) vs fp32 torch on the same bf16 inputs."""
     from pika_b200 import engine as E
     D = heads * 64
     prev = E.get_precision()
