@@ -89,11 +89,13 @@ def build_parser():
     parser = build_rnnt_parser()
     parser.description = 'Transducer MBR training'
     parser.add_argument('--beam_size', type=int, default=8, help='beam size to generate nbest')
-    parser.add_argument('--rnnt_scale', type=float, default=1.0, help='weight of the RNN-T loss next to the MBR loss')
+    parser.add_argument('--rnnt_scale', type=float, default=0.01, help='weight of the RNN-T loss next to the MBR loss')
     parser.add_argument('--lm', type=str, default='', help='LM for shallow fusion during N-best generation (not supported: FST fusion is --lm_scorer of the decoder)')
-    parser.add_argument('--lm_scale', type=float, default=1.0)
+    parser.add_argument('--lm_scale', type=float, default=0.1)
     parser.add_argument('--sm_scale', type=float, default=1.0, help='softmax smoothing of the N-best generation and of the MBR branch')
     parser.add_argument('--blk', type=int, default=0)
+    # defaults the reference's MBR script sets differently from its RNN-T script (trainer/train_transducer_mbr_bmuf_otfaug.py:340-420)
+    parser.set_defaults(num_epochs=3, num_batches_per_epoch=100000, sync_period=5)
     return parser
 
 
