@@ -177,6 +177,8 @@ def _cpu_worker(argv):
     a = parse_from(argv)
     if a.workload == "decode":
         return _cpu_decode_worker(a)
+    if a.workload == "mbr":
+        return _cpu_mbr_worker(a)
     fn, cores = cpu_step_fn(a)
     t0 = time.time()
     first = None
@@ -234,7 +236,7 @@ def run_cpu_bounded(a, warmup, steps, budget_s, threads=0, extra=None):
             continue
         if "step_s" in d:
             times.append(d["step_s"])
-        if extra is not None and ("first_step" in d or "decode" in d):
+        if extra is not None and ("first_step" in d or "decode" in d or "mbr" in d):
             extra.update(d)
         if "done" in d:
             cores = d["cores"]
@@ -276,6 +278,8 @@ def run_reference(a):
         return
     if a.workload == "decode":
         return run_reference_decode(a)
+    if a.workload == "mbr":
+        return run_reference_mbr(a)
     budget = 240.0
     # thread count: one probing step at each candidate, then the timed run with the faster
     probe = {}
@@ -643,6 +647,63 @@ def cpu_baseline_decode(a, budget_s):
             "sample": sample + "; %d beam steps in %.1f s" % (best["steps"], best["wall_s"])}
 
 
+def _cpu_mbr_worker(a):
+    """CPU arm of the MBR workload: one utterance (the bounded sample) through the oracle ports of its three parts -- N-best generation
+    (oracle/decode.py: beam, n_best = beam, no pruning, eval-mode encoder), the shared-encoder RNN-T branch and the path-gathered MBR
+    branch with backward (oracle/mbr.py, pinned to the reference's loop body), inf-norm clip + Nesterov SGD (oracle/train.py)."""
+    import numpy as np
+    import torch
+    from oracle import decode as od, mbr as ombr, model as om, train as ot
+    cores = a.cpu_threads if a.cpu_threads > 0 else min(os.cpu_count() or 1, CPU_THREADS_CAP)
+    torch.set_num_threads(cores)
+    beam = a.beam or 4
+    m = decode_model(a, None)
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in m.state_dict().items()}
+    x = torch.from_numpy(decode_feats(1, a.T, 11))
+    tgt = torch.from_numpy(np.random.default_rng(3).integers(1, a.V, (1, a.U)).astype(np.int64))
+    tl, ul = np.array([tprime(a.T)], np.int32), np.array([a.U], np.int32)
+    t0 = time.time()
+    with torch.no_grad():
+        enc = om.encoder_forward({k: v.detach() for k, v in sd.items()}, x, train=False)
+        ret = od.decode_batch({k: v.detach() for k, v in sd.items()}, enc, [int(tl[0])], beam, n_best=beam, max_len=[int(tl[0]) + a.U + 3],
+                              sm_scale=0.8, beam_prune=False)
+    t_dec = time.time() - t0
+    hyps = [[h + [-1] for h in ret["predictions"][0]]]                     # the trainer sees alignments that end in EOS (:176-181)
+    hyps = [[[t for t in h if t != -1] for h in hyps[0]]]
+    mbr, costs = ombr.mbr_loss_and_grads(sd, x, tgt, tl, ul, hyps, [ret["scores"][0]], 0, a.V, 0.5, 0.8)
+    params = [v for v in sd.values() if v.requires_grad and v.grad is not None]
+    tot, coef = ot.clip_coef_inf([p.grad.numpy() for p in params], 3.0)
+    with torch.no_grad():
+        for p_ in params:
+            p_.add_(p_.grad * float(coef), alpha=-1e-5)                    # first SGD step: the momentum buffer equals the gradient
+    dt = time.time() - t0
+    print(json.dumps({"mbr": {"utt_s": 1.0 / dt, "wall_s": dt, "decode_s": t_dec, "cores": cores, "mbr_loss": mbr,
+                              "hyp_len": [len(h) for h in hyps[0]]}}), flush=True)
+    print(json.dumps({"progress": 1, "step_s": dt}), flush=True)
+    print(json.dumps({"done": 1, "first_s": dt, "total_s": dt, "cores": cores}), flush=True)
+
+
+def cpu_baseline_mbr(a, budget_s):
+    extra = {}
+    run_cpu_bounded(a, 0, 1, budget_s, threads=min(os.cpu_count() or 1, CPU_THREADS_CAP), extra=extra)
+    d = extra.get("mbr")
+    sample = ("B=1 utterance (T=%d,U=%d,V=%d, beam %d) through the oracle ports of the MBR batch: N-best generation, RNN-T branch, MBR branch, "
+              "backward, clip + SGD (torch-CPU fp32, %d threads), one step, no warm-up" % (a.T, a.U, a.V, a.beam or 4, min(os.cpu_count() or 1, CPU_THREADS_CAP)))
+    if d is None:
+        return {"value": None, "unit": "utt/s", "cores": min(os.cpu_count() or 1, CPU_THREADS_CAP), "kind": "port",
+                "sample": sample + "; did not finish in %.0f s" % budget_s}
+    return {"value": d["utt_s"], "unit": "utt/s", "cores": d["cores"], "kind": "port",
+            "sample": sample + "; %.1f s of which N-best generation %.1f s" % (d["wall_s"], d["decode_s"])}
+
+
+def run_reference_mbr(a):
+    cb = cpu_baseline_mbr(a, 280.0)
+    print(json.dumps({"impl": "reference", "metric": MBR_METRIC, "value": cb["value"], "unit": "utt/s", "n_gpus": a.gpus, "steps": 1, "warmup": 0,
+                      "ms_per_step": (1e3 / cb["value"]) if cb["value"] else None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": {"workload": mbr_workload(a)}, "cpu_baseline": cb,
+                      "e2e": {"value": cb["value"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 def run_reference_decode(a):
     cb = cpu_baseline_decode(a, 280.0)
     print(json.dumps({"impl": "reference", "metric": DECODE_METRIC, "value": cb["value"], "unit": "RTF", "n_gpus": a.gpus, "steps": 1, "warmup": 0,
@@ -875,6 +936,11 @@ def run_mbr(a):
            "gpu_launches": launches}
     if params_identical is not None:
         res["params_identical_after_sync"] = params_identical
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            res["cpu_baseline"] = cpu_baseline_mbr(a, a.cpu_budget_s)
+        except Exception as ex:
+            res["cpu_baseline"] = {"error": repr(ex)}
     print(json.dumps(res))
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
