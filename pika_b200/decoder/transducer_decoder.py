@@ -351,9 +351,11 @@ class TransducerDecoder():
             act = ln > j
             toks[act, j] = ny[j + 1, sb[act], kk[act]]
             kk[act] = pk[j, sb[act], kk[act]]
-        ret = {"predictions": [[] for _ in range(B)], "scores": [[] for _ in range(B)]}
+        # "alignments" (extension): the same hypotheses as int64 arrays, for callers that post-process them in bulk (the MBR trainer)
+        ret = {"predictions": [[] for _ in range(B)], "scores": [[] for _ in range(B)], "alignments": [[] for _ in range(B)]}
         for r, (b, i) in enumerate(sel):
-            hyp = torch.from_numpy(toks[r, :max(int(ln[r]) - 1, 0)].copy())   # strip the ending eos(-1)
-            ret["predictions"][b].append(list(hyp.unbind(0)))                 # 0-d int64 tensors, like the reference's token lists
+            arr = toks[r, :max(int(ln[r]) - 1, 0)].copy()                     # strip the ending eos(-1)
+            ret["alignments"][b].append(arr)
+            ret["predictions"][b].append(list(torch.from_numpy(arr).unbind(0)))   # 0-d int64 tensors, like the reference's token lists
             ret["scores"][b].append(torch.tensor(float(fs[b, i]), dtype=torch.float32))
         return ret, enc.float()

@@ -21,7 +21,8 @@ from .. import kernels as K
 
 
 def edit_distance(a, b):
-    """Levenshtein distance between two int sequences (``editdistance.eval``, :188)."""
+    """Levenshtein distance between two int sequences (``editdistance.eval``, :188); scalar form, kept as the definition the batched
+    routine is tested against."""
     la, lb = len(a), len(b)
     prev = list(range(lb + 1))
     for i in range(1, la + 1):
@@ -33,20 +34,82 @@ def edit_distance(a, b):
     return prev[lb]
 
 
+def edit_distance_batch(refs, hyps):
+    """Levenshtein distances of P (reference, hypothesis) pairs at once: one numpy pass per reference position over a [P, Lmax + 1]
+    table.  The in-row dependency ``cur[j] = min(tmp[j], cur[j-1] + 1)`` is a prefix minimum: ``cur = cummin(tmp - j) + j``.
+    (The pure-Python double loop costs ~0.5 s for 64 hypotheses of 150 labels -- the reference calls a C library here.)"""
+    P = len(refs)
+    if P == 0:
+        return np.zeros(0, np.int64)
+    la = np.array([len(r) for r in refs], np.int64)
+    lb = np.array([len(h) for h in hyps], np.int64)
+    La, Lb = int(la.max()), int(lb.max())
+    A = np.full((P, max(La, 1)), -1, np.int64)
+    Bm = np.full((P, max(Lb, 1)), -2, np.int64)
+    for p in range(P):
+        A[p, :la[p]] = refs[p]
+        Bm[p, :lb[p]] = hyps[p]
+    idx = np.arange(Lb + 1, dtype=np.int64)
+    prev = np.broadcast_to(idx, (P, Lb + 1)).copy()                            # row 0: distance to the empty reference prefix
+    out = prev[np.arange(P), lb].copy()                                        # pairs with an empty reference
+    for i in range(1, La + 1):
+        tmp = np.empty_like(prev)
+        tmp[:, 0] = i
+        if Lb:
+            sub = prev[:, :-1] + (A[:, i - 1:i] != Bm[:, :Lb])
+            tmp[:, 1:] = np.minimum(prev[:, 1:] + 1, sub)
+        cur = np.minimum.accumulate(tmp - idx, axis=1) + idx
+        done = la == i
+        if done.any():
+            out[done] = cur[done, lb[done]]
+        prev = cur
+    return out
+
+
+def _tokens(h):
+    """one hypothesis (alignment incl. blanks) as an int64 array: accepts an array, a list of ints or a list of 0-d tensors"""
+    if isinstance(h, np.ndarray):
+        return h.astype(np.int64)
+    if len(h) and torch.is_tensor(h[0]):
+        return torch.stack(list(h)).cpu().numpy().astype(np.int64)
+    return np.asarray(list(h), dtype=np.int64).reshape(-1)
+
+
 def nbest_risk(hyps, scores, targets, ali_lens, blk):
     """host side of :171-195.  -> (hyps_nonblk, prob [bsz,beam], dist [bsz,beam], seq_grad [bsz,beam], mbr_loss)"""
     bsz, beam = len(hyps), len(hyps[0])
     sc = np.array([[float(s) for s in row] for row in scores], dtype=np.float32)
     e = np.exp(sc - sc.max(axis=1, keepdims=True))
     prob = (e / e.sum(axis=1, keepdims=True)).astype(np.float32)
-    nonblk = [[[int(t) for t in h if int(t) != blk] for h in row] for row in hyps]
-    dist = np.zeros((bsz, beam), np.float32)
-    for i in range(bsz):
-        ref = [int(v) for v in targets[i][:int(ali_lens[i])]]
-        for j in range(beam):
-            dist[i, j] = edit_distance(ref, nonblk[i][j])
+    arrs = [[_tokens(h) for h in row] for row in hyps]
+    nonblk = [[a[a != blk].tolist() for a in row] for row in arrs]
+    refs = [[int(v) for v in targets[i][:int(ali_lens[i])]] for i in range(bsz)]
+    dist = edit_distance_batch([refs[i] for i in range(bsz) for _ in range(beam)],
+                               [nonblk[i][j] for i in range(bsz) for j in range(beam)]).reshape(bsz, beam).astype(np.float32)
     avg = (prob * dist).sum(axis=1, keepdims=True)
     return nonblk, prob, dist, prob * (dist - avg), float(avg.sum())
+
+
+def alignment_nodes(hyps, seq_grad, Tp, U, blk):
+    """The (frame, label) lattice node every alignment token sits on (:197-232) and its gradient coefficient (:234: blank entries
+    divided by T'), for all hypotheses at once: token p of hypothesis (i, j) is emitted at frame #blanks-before-p and label position
+    #labels-before-p.  -> (ex_idx, py_idx, tokens, coef) flat arrays in (i, j, p) order."""
+    bsz, beam = len(hyps), len(hyps[0])
+    U1 = U + 1
+    ex, py, tk, cf = [], [], [], []
+    for i in range(bsz):
+        for j in range(beam):
+            h = _tokens(hyps[i][j])
+            isb = h == blk
+            t_i = np.cumsum(isb) - isb                                          # exclusive counts
+            u_i = np.cumsum(~isb) - (~isb)
+            sg = float(seq_grad[i, j])
+            ex.append(i * Tp + np.minimum(t_i, Tp - 1))
+            py.append((i * beam + j) * U1 + np.minimum(u_i, U))
+            tk.append(h)
+            cf.append(np.where(isb, np.float32(sg / float(Tp)), np.float32(sg)).astype(np.float32))
+    cat = lambda v, dt: np.concatenate(v).astype(dt) if v else np.zeros(0, dt)   # noqa: E731
+    return cat(ex, np.int32), cat(py, np.int32), cat(tk, np.int32), cat(cf, np.float32)
 
 
 def mbr_forward_backward(model, feats, target, len_batch, ali_lens, ret, blk=0, rnnt_scale=1.0, sm_scale=1.0):
@@ -54,7 +117,7 @@ def mbr_forward_backward(model, feats, target, len_batch, ali_lens, ret, blk=0, 
     feats [bsz,T,D] (already CMVN'd / SpecAugmented), target [bsz,Umax] int64 (padded with padding_idx),
     ret = decode_batch output with n_best == beam.  Returns (mbr_loss, rnnt_loss) as python floats / tensor."""
     dev = feats.device
-    hyps, scores = ret["predictions"], ret["scores"]
+    hyps, scores = ret.get("alignments") or ret["predictions"], ret["scores"]   # arrays when the decoder provides them (bulk host work)
     bsz, beam = len(hyps), len(hyps[0])
     bb = bsz * beam
     pad = model.embed.padding_idx
@@ -91,26 +154,11 @@ def mbr_forward_backward(model, feats, target, len_batch, ali_lens, ret, blk=0, 
     del logits, st
 
     # ---- MBR branch: alignment nodes of every hypothesis
-    ex_idx, py_idx, toks, coef = [], [], [], []
     U1 = U + 1
-    for i in range(bsz):
-        for j in range(beam):
-            h = [int(t) for t in hyps[i][j]]
-            t_i = u_i = 0
-            sg = float(seq_grad[i, j])
-            for p, tk in enumerate(h):
-                ex_idx.append(i * Tp + min(t_i, Tp - 1))
-                py_idx.append((i * beam + j) * U1 + min(u_i, U))
-                toks.append(tk)
-                coef.append(sg / float(Tp) if tk == blk else sg)                # blank gradients scaled by 1/T (:234)
-                if tk == blk:
-                    t_i += 1
-                else:
-                    u_i += 1
-    rows = len(toks)
-    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
-    ex_idx_t, py_idx_t, tok_t = i32(ex_idx), i32(py_idx), i32(toks)
-    coef_t = torch.tensor(coef, dtype=torch.float32, device=dev)
+    ex_idx, py_idx, toks, coef = alignment_nodes(hyps, seq_grad, Tp, U, blk)
+    rows = int(toks.shape[0])
+    ex_idx_t, py_idx_t, tok_t = (torch.from_numpy(v).to(dev) for v in (ex_idx, py_idx, toks))
+    coef_t = torch.from_numpy(coef).to(dev)
     fc1, fcg, fc2 = model.fc1, model.fc_gate, model.fc2
     wx = engine.stage_weight([fc1.weight, fcg.weight])
     w2 = engine.stage_weight(fc2.weight)
