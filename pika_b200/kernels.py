@@ -7,7 +7,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_RELU, AUX_ADD, AUX_MASK_NZ, AUX_NONE, PK_BF16, PK_F32, SEL_KZ, SEL_ZB0, SEL_ZB1,
+from ._lib import (ACT_NONE, ACT_RELU, AUX_ADD, AUX_MASK_NZ, AUX_NONE, PK_BF16, PK_F32, SEL_KZ, SEL_ZB0, SEL_ZB1,  # noqa: F401  (re-exported: engine uses K.ACT_RELU ...)
                    SEL_ZERO, GemmDesc, View4, check, lib)
 
 

@@ -4,12 +4,10 @@ sm_100a kernels: H2D of raw PCM -> on-GPU augmentation + fbank + splice + CMN/CM
 encoder / prediction net / fused joint+loss forward and backward -> inf-norm clip + Nesterov SGD ->
 BMUF block sync every ``sync_period`` batches.
 """
-import torch
 
 from .. import engine
-from ..frontend import Frontend
-from .flat import FlatParams, SgdNesterovClip, lr_at
-from .bmuf import BmufTrainer, SUCCESS
+from .flat import lr_at
+from .bmuf import SUCCESS
 
 
 def encoder_out_lens(lens, lctx, rctx, stride):

@@ -11,7 +11,6 @@ What runs underneath: raw-PCM loader threads -> GPU front end -> sm_100a model /
 """
 import argparse
 import importlib
-import math
 import os
 import sys
 

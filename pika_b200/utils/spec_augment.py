@@ -6,7 +6,6 @@ seeded like the reference draws identical masks.  ``draw()`` exposes the draw so
 end can apply the masks inside its last kernel instead of two slice writes + two host syncs.
 """
 import numpy as np
-import torch
 from torch.distributions.uniform import Uniform
 
 
