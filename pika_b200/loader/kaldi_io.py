@@ -105,11 +105,42 @@ def _read_token(f):
         tok += c
 
 
+def _read_compressed_matrix(f, fmt):
+    """Kaldi CompressedMatrix payload after its token (matrix/compressed-matrix.h): float min_value, float range, int32 rows, int32 cols
+    (the 'format' field of the global header is not written, the token carries it), then
+      CM  (format 1, what make_fbank.sh / copy-feats --compress=true write): per column four uint16 percentiles (0, 25, 75, 100 % as
+          min + range * v / 65535), then one byte per element, column-major; a byte decodes piecewise linearly between the percentiles
+          (v <= 64 | 64 < v <= 192 | v > 192);
+      CM2 (format 2): uint16 per element, row-major, min + range * v / 65535;   CM3 (format 3): uint8, min + range * v / 255."""
+    vmin, vrange = struct.unpack("<ff", f.read(8))
+    rows, cols = struct.unpack("<ii", f.read(8))
+    if fmt == 1:
+        pc = np.frombuffer(f.read(cols * 8), dtype=np.uint16).reshape(cols, 4).astype(np.float32)
+        pc = np.float32(vmin) + np.float32(vrange) * np.float32(1.52590218966964e-05) * pc          # [cols, 4]: p0, p25, p75, p100
+        d = np.frombuffer(f.read(cols * rows), dtype=np.uint8).reshape(cols, rows).astype(np.float32)
+        p0, p25, p75, p100 = (pc[:, i:i + 1] for i in range(4))
+        out = np.where(d <= 64, p0 + (p25 - p0) * d * np.float32(1 / 64.0),
+                       np.where(d <= 192, p25 + (p75 - p25) * (d - 64) * np.float32(1 / 128.0),
+                                p75 + (p100 - p75) * (d - 192) * np.float32(1 / 63.0)))
+        return np.ascontiguousarray(out.T, dtype=np.float32)
+    if fmt == 2:
+        d = np.frombuffer(f.read(rows * cols * 2), dtype=np.uint16).reshape(rows, cols).astype(np.float32)
+        return (np.float32(vmin) + np.float32(vrange) * np.float32(1.52590218966964e-05) * d).astype(np.float32)
+    d = np.frombuffer(f.read(rows * cols), dtype=np.uint8).reshape(rows, cols).astype(np.float32)
+    return (np.float32(vmin) + np.float32(vrange) * np.float32(1.0 / 255.0) * d).astype(np.float32)
+
+
 def _read_binary_matrix(f):
-    """after ``\\0B``: 'FM ' | 'DM ' , \\4 <int32 rows> \\4 <int32 cols>, row-major data (Kaldi's uncompressed matrix layout)"""
+    """after ``\0B``: 'FM ' | 'DM ' , \4 <int32 rows> \4 <int32 cols>, row-major data (Kaldi's uncompressed matrix layout), or a
+    compressed matrix 'CM ' | 'CM2 ' | 'CM3 ' (the default of Kaldi's feature dumps)"""
     kind = f.read(3)
+    if kind == b"CM ":
+        return _read_compressed_matrix(f, 1)
+    if kind in (b"CM2", b"CM3"):
+        assert f.read(1) == b" "
+        return _read_compressed_matrix(f, 2 if kind == b"CM2" else 3)
     if kind not in (b"FM ", b"DM "):
-        raise NotImplementedError("Kaldi matrix type %r (compressed matrices are not written by the recipes' feature dumps)" % kind)
+        raise NotImplementedError("Kaldi matrix type %r" % kind)
     assert f.read(1) == b"\4"
     rows = struct.unpack("<i", f.read(4))[0]
     assert f.read(1) == b"\4"

@@ -178,3 +178,51 @@ def test_read_fst_text(tmp_path):
     m = SortedMatcher((arcs, finals), 2, 6, 1, [])
     sc, st = m.get_scores(1, 3)                                # no arc 3 in state 1 -> back off (label 1) to state 0, then arc 3
     assert st == [2] and abs(sc[0] - 2.0) < 1e-12
+
+
+def _kaldi_compress_format1(mat):
+    """CompressedMatrix format 1 as Kaldi writes it (matrix/compressed-matrix.cc: ComputeColHeader / CompressColumn), restated for the
+    test: global (min, range), per-column 0/25/75/100 percentiles as uint16, bytes piecewise linear between them"""
+    rows, cols = mat.shape
+    vmin, vmax = float(mat.min()), float(mat.max())
+    vrange = max(vmax - vmin, 1e-30)
+    to_u16 = lambda v: int(np.clip(np.floor((v - vmin) / vrange * 65535.0 + 0.499), 0, 65535))      # noqa: E731
+    hdr, data = [], np.zeros((cols, rows), np.uint8)
+    for c in range(cols):
+        col = np.sort(mat[:, c])
+        q = [col[0], col[rows // 4], col[3 * rows // 4], col[-1]]
+        u = [to_u16(v) for v in q]
+        u[0] = min(u[0], 65532)                                   # strictly increasing percentiles, as Kaldi enforces them
+        u[1] = min(max(u[1], u[0] + 1), 65533); u[2] = min(max(u[2], u[1] + 1), 65534); u[3] = min(max(u[3], u[2] + 1), 65535)
+        p = [vmin + vrange * x / 65535.0 for x in u]
+        hdr.append(u)
+        for r in range(rows):
+            v = float(mat[r, c])
+            if v < p[1]:
+                b = int(np.clip(np.floor((v - p[0]) / (p[1] - p[0]) * 64 + 0.5), 0, 64))
+            elif v < p[2]:
+                b = int(np.clip(np.floor(64 + (v - p[1]) / (p[2] - p[1]) * 128 + 0.5), 64, 192))
+            else:
+                b = int(np.clip(np.floor(192 + (v - p[2]) / (p[3] - p[2]) * 63 + 0.5), 192, 255))
+            data[c, r] = b
+    return struct.pack("<ffii", vmin, vrange, rows, cols) + np.asarray(hdr, np.uint16).tobytes() + data.tobytes()
+
+
+def test_compressed_feature_archives(tmp_path):
+    """Kaldi's feature dumps are compressed by default (make_fbank.sh, copy-feats --compress=true): 'CM ' (one byte per element with
+    per-column percentile headers), 'CM2' (uint16) and 'CM3' (uint8) decode to within their quantisation step"""
+    from pika_b200.loader.kaldi_io import read_float_matrix_table
+    rng = np.random.default_rng(4)
+    mat = (rng.standard_normal((37, 8)) * 3.0 + 5.0).astype(np.float32)
+    vmin, vrange = float(mat.min()), float(mat.max() - mat.min())
+    ark = tmp_path / "cm.ark"
+    with open(ark, "wb") as f:
+        f.write(b"u1 \0BCM " + _kaldi_compress_format1(mat))
+        f.write(b"u2 \0BCM2 " + struct.pack("<ffii", vmin, vrange, 37, 8) + np.round((mat - vmin) / vrange * 65535).astype(np.uint16).tobytes())
+        f.write(b"u3 \0BCM3 " + struct.pack("<ffii", vmin, vrange, 37, 8) + np.round((mat - vmin) / vrange * 255).astype(np.uint8).tobytes())
+    got = dict(read_float_matrix_table("ark:%s" % ark))
+    assert list(got) == ["u1", "u2", "u3"] and all(v.shape == (37, 8) and v.dtype == np.float32 for v in got.values())
+    col_rng = mat.max(0) - mat.min(0)
+    assert (np.abs(got["u1"] - mat).max(0) <= col_rng / 64.0 + 1e-3).all()       # coarsest segment: a quarter of the column range / 64 steps
+    assert np.abs(got["u2"] - mat).max() <= vrange / 65535.0 + 1e-5
+    assert np.abs(got["u3"] - mat).max() <= vrange / 255.0 * 0.51 + 1e-5
